@@ -1,0 +1,153 @@
+/*
+ * qcat_b200.h -- C ABI of libqcat_b200.so, the B200 (sm_100a) replacement for qcat's per-read
+ * adapter / barcode alignment hot path.
+ *
+ * What it replaces in the reference (nanoporetech/qcat 1.1.0, paths relative to its checkout):
+ *   - the in-process FFI the reference itself uses: parasail-python (ctypes) ->
+ *     parasail_sg_striped_32(s1, s1Len, s2, s2Len, open, gap, matrix) called at
+ *     qcat/scanner_base.py:111-117 (barcodes) and :214-218 (adapters)      -> qcb_sg_batch()
+ *   - the Python loops around it: find_best_adapter_template (scanner_base.py:313-359),
+ *     extract_barcode_region (:29-60), find_highest_scoring_barcode (:63-141),
+ *     BarcodeScannerEPI2ME.scan (scanner_epi2me.py:33-144), BarcodeScannerDual.scan
+ *     (scanner_dual.py:35-146) and BarcodeScanner.detect_barcode (scanner_base.py:521-604),
+ *     batched over reads as in detect_barcode_batch (:714-733)              -> qcb_detect*()
+ *   - detect_kit's per-read vote (scanner_base.py:618-678)                  -> qcb_kit_vote*()
+ *   - the per-barcode counts behind the CLI histogram (cli.py:386-405)      -> qcb_histogram_device()
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every buffer; functions returning int
+ * return 0 on success and non-zero on error, with a thread-local message in qcb_last_error(); nothing
+ * throws across the boundary; a plan is immutable after creation and supports one call in flight.
+ * Entry points ending in _device take device pointers and a cudaStream_t (as void*) and do not
+ * synchronise; the others take host pointers and return when the results are in the caller's buffers.
+ * There is no CPU fallback: every compute entry point fails if no CUDA device is usable.
+ */
+#ifndef QCAT_B200_H
+#define QCAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QCB_MODE_EPI2ME 0
+#define QCB_MODE_DUAL 1
+
+/* Flattened scanner description (built by qcat_b200/tables.py).  All pointers are host pointers and are
+ * copied by qcb_plan_create(). */
+typedef struct {
+    /* qcatConfig, config.py:12-26 */
+    int32_t max_align_length;              /* W (150) */
+    int32_t barcode_extension;             /* extracted_barcode_extension (11) */
+    int32_t adapter_open, adapter_extend;  /* gap_open / gap_extend (2 / 2) */
+    int32_t barcode_open, barcode_extend;  /* 1 / 1, scanner_base.py:115-116 */
+    int32_t amat_size;                     /* adapter substitution matrix, amat_size^2 row-major ints */
+    const int32_t *amat;
+    const uint8_t *amap;                   /* 256-entry byte -> matrix index */
+    int32_t bmat_size;                     /* barcode substitution matrix */
+    const int32_t *bmat;
+    const uint8_t *bmap;
+    const uint8_t *comp;                   /* 256-entry complement table, utils.py:26-27 */
+    /* scanner */
+    int32_t mode;                          /* QCB_MODE_* */
+    double min_quality;
+    /* layouts in self.layouts order */
+    int32_t n_layouts;
+    const int32_t *adapter_off;            /* [n_layouts + 1] */
+    const uint8_t *adapter_seq;            /* N-masked adapter templates */
+    const double *denom;                   /* [n_layouts] score normaliser, scanner_base.py:308-310 */
+    const int32_t *bc_end;                 /* [n_layouts * 2] */
+    const int32_t *bc_len;                 /* [n_layouts * 2] */
+    const int32_t *group;                  /* [n_layouts * 2] template group of barcode set k, -1 = None */
+    const int32_t *trim_offset;            /* [n_layouts] */
+    const int32_t *is_double;              /* [n_layouts] */
+    /* template groups (up_context + barcode + down_context, in barcode-set order) */
+    int32_t n_groups;
+    const int32_t *group_off;              /* [n_groups + 1] */
+    const int32_t *tmpl_off;               /* [n_templates + 1] */
+    const uint8_t *tmpl_seq;
+    const int32_t *tmpl_ident;             /* [n_templates] equality class of Barcode.id */
+} qcb_tables;
+
+/* One record per read == build_return_dict (scanner_base.py:362-390).  32 bytes. */
+typedef struct {
+    int32_t layout;         /* index of result['adapter'] in the tables' layouts, -1 = None */
+    int32_t barcode;        /* index inside the layout's template group, -1 = None; dual: idx1 * n2 + idx2 */
+    double  barcode_score;
+    int32_t adapter_end;
+    int32_t trim5p;
+    int32_t trim3p;
+    int32_t exit_status;    /* 0 ok, 1 none, 1002 conflicting ends */
+} qcb_result;
+
+typedef struct qcb_plan qcb_plan;
+
+/* Which kernels a plan selected, for reporting. */
+typedef struct {
+    int32_t device;
+    int32_t sm_count;
+    int32_t fast_adapter;   /* 1 = packed u16x2 linear-gap adapter kernel, 0 = generic int32 affine kernel */
+    int32_t fast_barcode;   /* 1 = packed u16x2 shared-context barcode kernel, 0 = generic */
+    int32_t max_group_size;
+    int32_t n_templates;
+    int64_t workspace_bytes;
+    int64_t kernel_launches; /* kernels launched by this plan so far */
+} qcb_plan_info_t;
+
+int         qcb_device_count(void);
+const char *qcb_last_error(void);
+const char *qcb_version(void);
+
+qcb_plan *qcb_plan_create(const qcb_tables *tables, int device);
+void      qcb_plan_destroy(qcb_plan *plan);
+int       qcb_plan_info(qcb_plan *plan, qcb_plan_info_t *out);
+/* 0 = automatic (fast kernels when the scoring scheme allows), 1 = force the generic kernels. */
+int       qcb_plan_set_force_generic(qcb_plan *plan, int force);
+
+/* Batched semi-global alignment, every query against every reference: out[q * n_refs + r].
+ * Replaces parasail.sg_striped_32 (scanner_base.py:111-117, 214-218).  Host buffers. */
+int qcb_sg_batch(int device,
+                 const uint8_t *queries, const int32_t *query_off, int32_t n_queries,
+                 const uint8_t *refs, const int32_t *ref_off, int32_t n_refs,
+                 int32_t open, int32_t extend,
+                 const int32_t *matrix, int32_t msize, const uint8_t *mapper,
+                 int32_t *score, int32_t *end_query, int32_t *end_ref);
+
+/* detect_barcode for n_reads reads given as their two windows (see qcat_b200/tables.py:pack_windows):
+ * win5[i] = read[:W], tail3[i] = read[-W:] (not reverse-complemented), slots of `stride` bytes
+ * (stride >= W, multiple of 16), wlen[i] = min(len, W), read_len[i] = len(read).
+ * subset = the layout indices to consider ("kits", scanner_base.py:526-529); NULL/0 = all layouts. */
+int qcb_detect(qcb_plan *plan, const uint8_t *win5, const uint8_t *tail3, int32_t stride,
+               const int32_t *wlen, const int64_t *read_len, int64_t n_reads,
+               const int32_t *subset, int32_t n_subset, qcb_result *out);
+
+int qcb_detect_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t *d_tail3, int32_t stride,
+                      const int32_t *d_wlen, const int64_t *d_read_len, int64_t n_reads,
+                      const int32_t *subset /* host */, int32_t n_subset, qcb_result *d_out, void *stream);
+
+/* BarcodeScanner.scan (scanner_epi2me.py:33-144 / scanner_dual.py:35-146) for n_windows already-oriented windows
+ * of any length (wlen[i] <= stride): one record per window with trim5p = trim3p = 0 and exit_status 0, or the
+ * empty record (layout -1, exit_status 1) where the reference returns empty_return_dict().  Host buffers. */
+int qcb_scan(qcb_plan *plan, const uint8_t *windows, int32_t stride, const int32_t *wlen, int64_t n_windows,
+             const int32_t *subset, int32_t n_subset, qcb_result *out);
+
+/* detect_kit's per-read vote over ALL layouts: layout index of the higher-scoring end (scanner_base.py:632-642). */
+int qcb_kit_vote(qcb_plan *plan, const uint8_t *win5, const uint8_t *tail3, int32_t stride,
+                 const int32_t *wlen, int64_t n_reads, int32_t *vote_layout);
+
+int qcb_kit_vote_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t *d_tail3, int32_t stride,
+                        const int32_t *d_wlen, int64_t n_reads, int32_t *d_vote_layout, void *stream);
+
+/* counts[bin] += 1 per record, bin = 0 for "none", 1 + layout_bin_base[layout] + barcode otherwise
+ * (layout_bin_base: host array [n_layouts]).  d_counts must hold n_bins int64 and is NOT cleared. */
+int qcb_histogram_device(qcb_plan *plan, const qcb_result *d_results, int64_t n_reads,
+                         const int32_t *layout_bin_base, int64_t *d_counts, int32_t n_bins, void *stream);
+
+/* Issue-rate micro-benchmark of the DP inner instruction pair on this device (compute-roofline
+ * denominator): packed 16-bit DP cell updates per second the SMs can issue. */
+int qcb_microbench_cell_rate(int device, double *cells_per_second, double *sm_mhz_effective);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

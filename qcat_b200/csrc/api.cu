@@ -1,0 +1,483 @@
+// C-ABI layer of libqcat_b200.so: plan (device tables + workspace), pipeline orchestration, host-buffer
+// entry points.  See include/qcat_b200.h for the contract and the reference interfaces each call replaces.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "plan.h"
+#include "kernels_generic.cuh"
+#include "kernels_fast.cuh"
+#include "microbench.cuh"
+
+using namespace qcb;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return 1;
+}
+
+#define QCB_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; bytes = 0;
+        size_t want = need + need / 4;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e != cudaSuccess) return fail("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        bytes = want;
+        return 0;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+};
+
+}  // namespace
+
+struct qcb_plan {
+    int device = 0;
+    int sm_count = 0;
+    bool force_generic = false;
+    DevTables t{};
+    void *slab = nullptr;            // device tables
+    size_t slab_bytes = 0;
+    std::vector<int32_t> h_group_off, h_group, h_tmpl_off, h_adapter_off;
+    int bmax0 = 0, bmax1 = 0;        // largest barcode set 0 / set 1 over all layouts
+    int max_adapter = 0, max_template = 0;
+    FastPlan fast;                   // packed-kernel tables (kernels_fast.cuh)
+    // workspace, sized per chunk of reads
+    DeviceBuffer wins, ad_score, ad_end, sel, bc_score, subset_dev, in_stage, out_stage, misc;
+    cudaStream_t stream = nullptr;   // used by the host-buffer entry points
+    long long launches = 0;
+    long long chunk_reads = 1 << 18;
+};
+
+namespace {
+
+template <typename T>
+size_t slab_put(std::vector<uint8_t> &slab, const T *src, size_t count)
+{
+    size_t off = (slab.size() + 15) / 16 * 16;
+    slab.resize(off + sizeof(T) * (count ? count : 1));
+    if (count) memcpy(slab.data() + off, src, sizeof(T) * count);
+    return off;
+}
+
+int upload_tables(qcb_plan *p, const qcb_tables *h)
+{
+    const int nl = h->n_layouts, ng = h->n_groups;
+    const int nt = ng > 0 ? h->group_off[ng] : 0;
+    std::vector<uint8_t> slab;
+    size_t o_amat = slab_put(slab, h->amat, (size_t)h->amat_size * h->amat_size);
+    size_t o_amap = slab_put(slab, h->amap, 256);
+    size_t o_bmat = slab_put(slab, h->bmat, (size_t)h->bmat_size * h->bmat_size);
+    size_t o_bmap = slab_put(slab, h->bmap, 256);
+    size_t o_comp = slab_put(slab, h->comp, 256);
+    size_t o_aoff = slab_put(slab, h->adapter_off, nl + 1);
+    size_t o_aseq = slab_put(slab, h->adapter_seq, nl ? h->adapter_off[nl] : 0);
+    size_t o_den = slab_put(slab, h->denom, nl);
+    size_t o_bce = slab_put(slab, h->bc_end, nl * 2);
+    size_t o_bcl = slab_put(slab, h->bc_len, nl * 2);
+    size_t o_grp = slab_put(slab, h->group, nl * 2);
+    size_t o_trm = slab_put(slab, h->trim_offset, nl);
+    size_t o_dbl = slab_put(slab, h->is_double, nl);
+    size_t o_goff = slab_put(slab, h->group_off, ng + 1);
+    size_t o_toff = slab_put(slab, h->tmpl_off, nt + 1);
+    size_t o_tseq = slab_put(slab, h->tmpl_seq, nt ? h->tmpl_off[nt] : 0);
+    size_t o_tid = slab_put(slab, h->tmpl_ident, nt);
+
+    QCB_CUDA(cudaMalloc(&p->slab, slab.size()));
+    p->slab_bytes = slab.size();
+    QCB_CUDA(cudaMemcpy(p->slab, slab.data(), slab.size(), cudaMemcpyHostToDevice));
+    const uint8_t *d = (const uint8_t *)p->slab;
+    DevTables &t = p->t;
+    t.W = h->max_align_length; t.ext = h->barcode_extension;
+    t.a_open = h->adapter_open; t.a_extend = h->adapter_extend;
+    t.b_open = h->barcode_open; t.b_extend = h->barcode_extend;
+    t.amat_size = h->amat_size; t.bmat_size = h->bmat_size;
+    t.mode = h->mode; t.n_layouts = nl; t.n_groups = ng; t.n_templates = nt;
+    t.min_quality = h->min_quality;
+    t.amat = (const int32_t *)(d + o_amat); t.amap = d + o_amap;
+    t.bmat = (const int32_t *)(d + o_bmat); t.bmap = d + o_bmap; t.comp = d + o_comp;
+    t.adapter_off = (const int32_t *)(d + o_aoff); t.adapter_seq = d + o_aseq;
+    t.denom = (const double *)(d + o_den);
+    t.bc_end = (const int32_t *)(d + o_bce); t.bc_len = (const int32_t *)(d + o_bcl);
+    t.group = (const int32_t *)(d + o_grp); t.trim_offset = (const int32_t *)(d + o_trm);
+    t.is_double = (const int32_t *)(d + o_dbl);
+    t.group_off = (const int32_t *)(d + o_goff); t.tmpl_off = (const int32_t *)(d + o_toff);
+    t.tmpl_seq = d + o_tseq; t.tmpl_ident = (const int32_t *)(d + o_tid);
+
+    p->h_group_off.assign(h->group_off, h->group_off + ng + 1);
+    p->h_group.assign(h->group, h->group + nl * 2);
+    p->h_tmpl_off.assign(h->tmpl_off, h->tmpl_off + nt + 1);
+    p->h_adapter_off.assign(h->adapter_off, h->adapter_off + nl + 1);
+    for (int L = 0; L < nl; ++L) {
+        p->max_adapter = std::max(p->max_adapter, h->adapter_off[L + 1] - h->adapter_off[L]);
+        for (int k = 0; k < 2; ++k) {
+            int g = h->group[L * 2 + k];
+            if (g < 0) continue;
+            int sz = h->group_off[g + 1] - h->group_off[g];
+            if (k == 0) p->bmax0 = std::max(p->bmax0, sz); else p->bmax1 = std::max(p->bmax1, sz);
+        }
+    }
+    for (int b = 0; b < nt; ++b) p->max_template = std::max(p->max_template, h->tmpl_off[b + 1] - h->tmpl_off[b]);
+    return 0;
+}
+
+int validate_tables(const qcb_tables *h)
+{
+    if (!h) return fail("tables is NULL");
+    if (h->n_layouts <= 0) return fail("no layouts in tables");
+    if (h->amat_size <= 0 || h->amat_size > kMaxMatrix || h->bmat_size <= 0 || h->bmat_size > kMaxMatrix)
+        return fail("substitution matrix size must be in [1, %d]", kMaxMatrix);
+    if (h->max_align_length <= 0) return fail("max_align_length must be positive");
+    if (h->mode != QCB_MODE_EPI2ME && h->mode != QCB_MODE_DUAL) return fail("unknown mode %d", h->mode);
+    for (int L = 0; L < h->n_layouts; ++L) {
+        int alen = h->adapter_off[L + 1] - h->adapter_off[L];
+        if (alen <= 0 || alen > kMaxTemplate) return fail("adapter %d length %d outside [1, %d]", L, alen, kMaxTemplate);
+        if (h->group[L * 2] < 0) return fail("layout %d has no barcode set", L);
+        if (h->mode == QCB_MODE_DUAL && h->group[L * 2 + 1] < 0) return fail("dual mode needs a second barcode set (layout %d)", L);
+    }
+    int nt = h->n_groups > 0 ? h->group_off[h->n_groups] : 0;
+    for (int b = 0; b < nt; ++b) {
+        int tl = h->tmpl_off[b + 1] - h->tmpl_off[b];
+        if (tl <= 0 || tl > kMaxTemplate) return fail("barcode template %d length %d outside [1, %d]", b, tl, kMaxTemplate);
+    }
+    for (int i = 0; i < 256; ++i)
+        if (h->amap[i] >= h->amat_size || h->bmap[i] >= h->bmat_size) return fail("mapper entry %d out of range", i);
+    return 0;
+}
+
+// Run the pipeline over one chunk of reads already resident on the device.
+// d_tail3 == nullptr selects window mode: d_win5 holds n already-oriented windows (BarcodeScanner.scan).
+int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int stride, const int32_t *d_wlen,
+              const int64_t *d_read_len, long long n, const int32_t *d_subset, const int32_t *h_subset, int n_subset,
+              qcb_result *d_out, int32_t *d_vote, cudaStream_t st)
+{
+    const bool window_mode = d_tail3 == nullptr;
+    const int wshift = window_mode ? 0 : 1;
+    const long long nw = window_mode ? n : 2 * n;
+    const DevTables &t = p->t;
+    const int bslots = p->bmax0 + (t.mode == QCB_MODE_DUAL ? p->bmax1 : 0);
+    if (!window_mode && p->wins.reserve((size_t)nw * stride)) return 1;
+    if (p->ad_score.reserve((size_t)nw * n_subset * 4)) return 1;
+    if (p->ad_end.reserve((size_t)nw * n_subset * 4)) return 1;
+    const uint8_t *wins = d_win5;
+    int32_t *ad_score = (int32_t *)p->ad_score.ptr, *ad_end = (int32_t *)p->ad_end.ptr;
+    if (!window_mode) {
+        k_orient<<<grid_for(nw * stride, 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, (uint8_t *)p->wins.ptr);
+        p->launches++;
+        wins = (const uint8_t *)p->wins.ptr;
+    }
+
+    const bool fast_ok = !p->force_generic && !window_mode && stride <= kFastMaxStride;
+    if (fast_ok && p->fast.adapter_ok) {
+        int rc = fast_adapter_stage(p->fast, t, wins, stride, d_wlen, nw, d_subset, h_subset, n_subset, ad_score, ad_end, st,
+                                    &p->launches);
+        if (rc) return fail("fast adapter stage launch failed");
+    } else {
+        k_adapter_generic<<<grid_for(nw * n_subset, 128), 128, 0, st>>>(t, wins, stride, d_wlen, wshift, nw, d_subset, n_subset,
+                                                                       ad_score, ad_end);
+        p->launches++;
+    }
+    if (d_vote) {
+        k_kit_vote<<<grid_for(n, 256), 256, 0, st>>>(t, d_wlen, n, d_subset, n_subset, ad_score, ad_end, d_vote);
+        p->launches++;
+        QCB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (p->sel.reserve((size_t)nw * sizeof(WindowSel))) return 1;
+    if (p->bc_score.reserve((size_t)nw * bslots * 4)) return 1;
+    WindowSel *sel = (WindowSel *)p->sel.ptr;
+    int32_t *bc_score = (int32_t *)p->bc_score.ptr;
+    k_select<<<grid_for(nw, 256), 256, 0, st>>>(t, d_wlen, wshift, nw, d_subset, n_subset, ad_score, ad_end, sel);
+    p->launches++;
+    if (fast_ok && p->fast.barcode_ok) {
+        int rc = fast_barcode_stage(p->fast, t, wins, stride, nw, sel, p->bmax0, bslots, bc_score, st, &p->launches);
+        if (rc) return fail("fast barcode stage launch failed");
+    } else {
+        k_barcode_generic<<<grid_for(nw * bslots, 128), 128, 0, st>>>(t, wins, stride, nw, sel, p->bmax0, bslots, bc_score);
+        p->launches++;
+    }
+    if (window_mode) k_scan_out<<<grid_for(nw, 128), 128, 0, st>>>(t, d_wlen, nw, sel, bc_score, p->bmax0, bslots, d_out);
+    else k_finalize<<<grid_for(n, 128), 128, 0, st>>>(t, d_wlen, d_read_len, n, sel, bc_score, p->bmax0, bslots, d_out);
+    p->launches++;
+    QCB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int prepare_subset(qcb_plan *p, const int32_t *subset, int n_subset, std::vector<int32_t> &h, cudaStream_t st)
+{
+    if (!subset || n_subset <= 0) {
+        h.resize(p->t.n_layouts);
+        for (int i = 0; i < p->t.n_layouts; ++i) h[i] = i;
+    } else {
+        h.assign(subset, subset + n_subset);
+        for (int v : h)
+            if (v < 0 || v >= p->t.n_layouts) return fail("layout subset entry %d out of range", v);
+    }
+    if (p->subset_dev.reserve(h.size() * 4)) return 1;
+    QCB_CUDA(cudaMemcpyAsync(p->subset_dev.ptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
+    // the host vector must outlive the async copy: pageable memcpy is staged synchronously by the runtime.
+    return 0;
+}
+
+int detect_device_impl(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int32_t stride, const int32_t *d_wlen,
+                       const int64_t *d_read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset,
+                       qcb_result *d_out, int32_t *d_vote, cudaStream_t st)
+{
+    if (!p) return fail("plan is NULL");
+    if (n_reads < 0) return fail("n_reads is negative");
+    if (d_tail3 && stride < p->t.W) return fail("stride %d smaller than max_align_length %d", stride, p->t.W);
+    QCB_CUDA(cudaSetDevice(p->device));
+    if (n_reads == 0) return 0;
+    std::vector<int32_t> h_subset;
+    if (prepare_subset(p, subset, n_subset, h_subset, st)) return 1;
+    const int32_t *d_subset = (const int32_t *)p->subset_dev.ptr;
+    long long dev_chunk = p->chunk_reads;
+    if ((long long)stride * dev_chunk > (1LL << 28)) dev_chunk = std::max<long long>(1, (1LL << 28) / stride);
+    for (long long off = 0; off < n_reads; off += dev_chunk) {
+        long long n = std::min<long long>(dev_chunk, n_reads - off);
+        if (run_chunk(p, d_win5 + off * stride, d_tail3 ? d_tail3 + off * stride : nullptr, stride, d_wlen + off,
+                      d_read_len ? d_read_len + off : nullptr, n, d_subset, h_subset.data(), (int)h_subset.size(),
+                      d_out ? d_out + off : nullptr, d_vote ? d_vote + off : nullptr, st))
+            return 1;
+    }
+    return 0;
+}
+
+// Host-buffer path: stage -> device pipeline -> copy back, chunk by chunk.
+int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int32_t stride, const int32_t *wlen,
+                     const int64_t *read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset,
+                     qcb_result *out, int32_t *vote)
+{
+    if (!p) return fail("plan is NULL");
+    if (n_reads < 0) return fail("n_reads is negative");
+    if (n_reads == 0) return 0;
+    const bool window_mode = tail3 == nullptr;
+    if (!win5 || !wlen || (!vote && !out) || (!vote && !window_mode && !read_len)) return fail("NULL input/output buffer");
+    QCB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = p->stream;
+    long long chunk = p->chunk_reads;
+    if ((long long)stride * chunk > (1LL << 28)) chunk = std::max<long long>(1, (1LL << 28) / stride);
+    for (long long off = 0; off < n_reads; off += chunk) {
+        long long n = std::min<long long>(chunk, n_reads - off);
+        size_t b_win = (size_t)n * stride, b_len = (size_t)n * 4, b_rl = (size_t)n * 8;
+        size_t o_tail = (b_win + 255) / 256 * 256, o_len = o_tail + (b_win + 255) / 256 * 256;
+        size_t o_rl = o_len + (b_len + 255) / 256 * 256, total = o_rl + b_rl;
+        if (p->in_stage.reserve(total)) return 1;
+        if (p->out_stage.reserve((size_t)n * (vote ? 4 : sizeof(qcb_result)))) return 1;
+        uint8_t *d = (uint8_t *)p->in_stage.ptr;
+        QCB_CUDA(cudaMemcpyAsync(d, win5 + off * stride, b_win, cudaMemcpyHostToDevice, st));
+        if (!window_mode) QCB_CUDA(cudaMemcpyAsync(d + o_tail, tail3 + off * stride, b_win, cudaMemcpyHostToDevice, st));
+        QCB_CUDA(cudaMemcpyAsync(d + o_len, wlen + off, b_len, cudaMemcpyHostToDevice, st));
+        if (!vote && !window_mode) QCB_CUDA(cudaMemcpyAsync(d + o_rl, read_len + off, b_rl, cudaMemcpyHostToDevice, st));
+        if (detect_device_impl(p, d, window_mode ? nullptr : d + o_tail, stride, (const int32_t *)(d + o_len), (const int64_t *)(d + o_rl), n,
+                               subset, n_subset, vote ? nullptr : (qcb_result *)p->out_stage.ptr,
+                               vote ? (int32_t *)p->out_stage.ptr : nullptr, st))
+            return 1;
+        if (vote) QCB_CUDA(cudaMemcpyAsync(vote + off, p->out_stage.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        else QCB_CUDA(cudaMemcpyAsync(out + off, p->out_stage.ptr, (size_t)n * sizeof(qcb_result), cudaMemcpyDeviceToHost, st));
+        QCB_CUDA(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qcb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *qcb_last_error(void) { return g_error.c_str(); }
+
+const char *qcb_version(void) { return "qcat_b200 0.1.0 (sm_100a)"; }
+
+qcb_plan *qcb_plan_create(const qcb_tables *tables, int device)
+{
+    if (validate_tables(tables)) return nullptr;
+    int ndev = qcb_device_count();
+    if (ndev <= 0) { fail("no CUDA device available (libqcat_b200 has no CPU fallback)"); return nullptr; }
+    if (device < 0 || device >= ndev) { fail("device %d out of range (%d devices)", device, ndev); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice(%d) failed", device); return nullptr; }
+    qcb_plan *p = new qcb_plan();
+    p->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { fail("cudaGetDeviceProperties failed"); delete p; return nullptr; }
+    p->sm_count = prop.multiProcessorCount;
+    if (upload_tables(p, tables)) { delete p; return nullptr; }
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { fail("stream creation failed"); delete p; return nullptr; }
+    if (fast_plan_build(p->fast, tables, p->sm_count)) { fail("fast-plan construction failed: %s", p->fast.error.c_str()); delete p; return nullptr; }
+    return p;
+}
+
+void qcb_plan_destroy(qcb_plan *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    fast_plan_free(p->fast);
+    p->wins.release(); p->ad_score.release(); p->ad_end.release(); p->sel.release(); p->bc_score.release();
+    p->subset_dev.release(); p->in_stage.release(); p->out_stage.release(); p->misc.release();
+    if (p->slab) cudaFree(p->slab);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int qcb_plan_info(qcb_plan *p, qcb_plan_info_t *out)
+{
+    if (!p || !out) return fail("NULL argument");
+    out->device = p->device; out->sm_count = p->sm_count;
+    out->fast_adapter = (!p->force_generic && p->fast.adapter_ok) ? 1 : 0;
+    out->fast_barcode = (!p->force_generic && p->fast.barcode_ok) ? 1 : 0;
+    out->max_group_size = std::max(p->bmax0, p->bmax1);
+    out->n_templates = p->t.n_templates;
+    out->workspace_bytes = (int64_t)(p->wins.bytes + p->ad_score.bytes + p->ad_end.bytes + p->sel.bytes + p->bc_score.bytes +
+                                     p->in_stage.bytes + p->out_stage.bytes + p->fast.workspace_bytes());
+    out->kernel_launches = p->launches;
+    return 0;
+}
+
+int qcb_plan_set_force_generic(qcb_plan *p, int force)
+{
+    if (!p) return fail("plan is NULL");
+    p->force_generic = force != 0;
+    return 0;
+}
+
+int qcb_sg_batch(int device, const uint8_t *queries, const int32_t *query_off, int32_t n_queries,
+                 const uint8_t *refs, const int32_t *ref_off, int32_t n_refs, int32_t open, int32_t extend,
+                 const int32_t *matrix, int32_t msize, const uint8_t *mapper,
+                 int32_t *score, int32_t *end_query, int32_t *end_ref)
+{
+    if (n_queries < 0 || n_refs < 0) return fail("negative count");
+    if (n_queries == 0 || n_refs == 0) return 0;
+    if (!queries || !query_off || !refs || !ref_off || !matrix || !mapper || !score || !end_query || !end_ref)
+        return fail("NULL buffer");
+    if (msize <= 0 || msize > kMaxMatrix) return fail("matrix size must be in [1, %d]", kMaxMatrix);
+    for (int i = 0; i < 256; ++i) if (mapper[i] >= msize) return fail("mapper entry %d out of range", i);
+    for (int r = 0; r < n_refs; ++r) {
+        int m = ref_off[r + 1] - ref_off[r];
+        if (m < 0 || m > kMaxTemplate) return fail("reference %d length %d outside [0, %d]", r, m, kMaxTemplate);
+    }
+    int ndev = qcb_device_count();
+    if (ndev <= 0) return fail("no CUDA device available (libqcat_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("device %d out of range", device);
+    QCB_CUDA(cudaSetDevice(device));
+    size_t qb = (size_t)query_off[n_queries], rb = (size_t)ref_off[n_refs];
+    size_t pairs = (size_t)n_queries * n_refs;
+    uint8_t *d_q = nullptr, *d_r = nullptr, *d_map = nullptr;
+    int32_t *d_qo = nullptr, *d_ro = nullptr, *d_mat = nullptr, *d_out = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() { cudaFree(d_q); cudaFree(d_r); cudaFree(d_map); cudaFree(d_qo); cudaFree(d_ro); cudaFree(d_mat); cudaFree(d_out); };
+#define SG_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail("%s failed: %s", #call, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
+    SG_CUDA(cudaMalloc(&d_q, qb + 16)); SG_CUDA(cudaMalloc(&d_r, rb + 16)); SG_CUDA(cudaMalloc(&d_map, 256));
+    SG_CUDA(cudaMalloc(&d_qo, (size_t)(n_queries + 1) * 4)); SG_CUDA(cudaMalloc(&d_ro, (size_t)(n_refs + 1) * 4));
+    SG_CUDA(cudaMalloc(&d_mat, (size_t)msize * msize * 4)); SG_CUDA(cudaMalloc(&d_out, pairs * 12));
+    SG_CUDA(cudaMemcpy(d_q, queries, qb, cudaMemcpyHostToDevice)); SG_CUDA(cudaMemcpy(d_r, refs, rb, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_map, mapper, 256, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_qo, query_off, (size_t)(n_queries + 1) * 4, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_ro, ref_off, (size_t)(n_refs + 1) * 4, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_mat, matrix, (size_t)msize * msize * 4, cudaMemcpyHostToDevice));
+    k_sg_batch<<<grid_for((long long)pairs, 128), 128>>>(d_q, d_qo, n_queries, d_r, d_ro, n_refs, open, extend, d_mat, msize, d_map,
+                                                        d_out, d_out + pairs, d_out + 2 * pairs);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaMemcpy(score, d_out, pairs * 4, cudaMemcpyDeviceToHost));
+    SG_CUDA(cudaMemcpy(end_query, d_out + pairs, pairs * 4, cudaMemcpyDeviceToHost));
+    SG_CUDA(cudaMemcpy(end_ref, d_out + 2 * pairs, pairs * 4, cudaMemcpyDeviceToHost));
+#undef SG_CUDA
+    cleanup();
+    return 0;
+}
+
+int qcb_detect(qcb_plan *plan, const uint8_t *win5, const uint8_t *tail3, int32_t stride, const int32_t *wlen,
+               const int64_t *read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset, qcb_result *out)
+{
+    return detect_host_impl(plan, win5, tail3, stride, wlen, read_len, n_reads, subset, n_subset, out, nullptr);
+}
+
+int qcb_detect_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t *d_tail3, int32_t stride, const int32_t *d_wlen,
+                      const int64_t *d_read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset,
+                      qcb_result *d_out, void *stream)
+{
+    if (!d_win5 || !d_tail3 || !d_wlen || !d_read_len || !d_out) return n_reads == 0 ? 0 : fail("NULL device buffer");
+    return detect_device_impl(plan, d_win5, d_tail3, stride, d_wlen, d_read_len, n_reads, subset, n_subset, d_out, nullptr,
+                              (cudaStream_t)stream);
+}
+
+int qcb_scan(qcb_plan *plan, const uint8_t *windows, int32_t stride, const int32_t *wlen, int64_t n_windows,
+             const int32_t *subset, int32_t n_subset, qcb_result *out)
+{
+    return detect_host_impl(plan, windows, nullptr, stride, wlen, nullptr, n_windows, subset, n_subset, out, nullptr);
+}
+
+int qcb_kit_vote(qcb_plan *plan, const uint8_t *win5, const uint8_t *tail3, int32_t stride, const int32_t *wlen,
+                 int64_t n_reads, int32_t *vote_layout)
+{
+    if (!vote_layout) return n_reads == 0 ? 0 : fail("NULL output buffer");
+    return detect_host_impl(plan, win5, tail3, stride, wlen, nullptr, n_reads, nullptr, 0, nullptr, vote_layout);
+}
+
+int qcb_kit_vote_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t *d_tail3, int32_t stride, const int32_t *d_wlen,
+                        int64_t n_reads, int32_t *d_vote_layout, void *stream)
+{
+    if (!d_win5 || !d_tail3 || !d_wlen || !d_vote_layout) return n_reads == 0 ? 0 : fail("NULL device buffer");
+    return detect_device_impl(plan, d_win5, d_tail3, stride, d_wlen, nullptr, n_reads, nullptr, 0, nullptr, d_vote_layout,
+                              (cudaStream_t)stream);
+}
+
+int qcb_histogram_device(qcb_plan *p, const qcb_result *d_results, int64_t n_reads, const int32_t *layout_bin_base,
+                         int64_t *d_counts, int32_t n_bins, void *stream)
+{
+    if (!p) return fail("plan is NULL");
+    if (n_reads <= 0) return 0;
+    if (!d_results || !layout_bin_base || !d_counts) return fail("NULL buffer");
+    QCB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->misc.reserve((size_t)p->t.n_layouts * 4)) return 1;
+    QCB_CUDA(cudaMemcpyAsync(p->misc.ptr, layout_bin_base, (size_t)p->t.n_layouts * 4, cudaMemcpyHostToDevice, st));
+    k_histogram<<<grid_for(n_reads, 256), 256, 0, st>>>(d_results, n_reads, (const int32_t *)p->misc.ptr,
+                                                       (unsigned long long *)d_counts, n_bins);
+    p->launches++;
+    QCB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int qcb_microbench_cell_rate(int device, double *cells_per_second, double *sm_mhz_effective)
+{
+    int ndev = qcb_device_count();
+    if (ndev <= 0) return fail("no CUDA device available");
+    if (device < 0 || device >= ndev) return fail("device %d out of range", device);
+    QCB_CUDA(cudaSetDevice(device));
+    std::string err;
+    if (microbench_cell_rate(cells_per_second, sm_mhz_effective, err)) return fail("%s", err.c_str());
+    return 0;
+}
+
+}  // extern "C"

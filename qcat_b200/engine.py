@@ -1,0 +1,187 @@
+"""Device plan: thin Python owner of a `qcb_plan` (include/qcat_b200.h).
+
+Inputs and outputs are numpy arrays (host entry points) or raw device pointers (device entry points, e.g.
+`tensor.data_ptr()` of torch tensors -- torch is only used by callers for device memory and streams).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from qcat_b200 import _ffi
+from qcat_b200.tables import Tables, pack_windows
+
+
+def default_device():
+    for key in ("QCAT_B200_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(key, "") != "":
+            return int(os.environ[key])
+    return 0
+
+
+def device_count():
+    return int(_ffi.load().qcb_device_count())
+
+
+def _vp(arr):
+    return ctypes.c_void_p(arr.ctypes.data)
+
+
+def sg_batch(queries, refs, open, extend, matrix, device=None):
+    """Every query against every reference with parasail `sg` semantics -> (score, end_query, end_ref) int32
+    arrays of shape (len(queries), len(refs)).  `matrix` is a ScoreMatrix or parasail-like Matrix."""
+    from qcat_b200.config import matrix_arrays
+    lib = _ffi.load()
+    msize, mat, mapper = matrix_arrays(matrix)
+
+    def concat(seqs):
+        raw = [s if isinstance(s, bytes) else s.encode("latin-1", "replace") for s in seqs]
+        off = np.zeros(len(raw) + 1, dtype=np.int32)
+        if raw:
+            off[1:] = np.cumsum([len(r) for r in raw])
+        buf = np.frombuffer(b"".join(raw) or b"\0", dtype=np.uint8).copy()
+        return buf, off
+
+    qbuf, qoff = concat(queries)
+    rbuf, roff = concat(refs)
+    shape = (len(queries), len(refs))
+    score = np.zeros(shape, dtype=np.int32)
+    end_query = np.zeros(shape, dtype=np.int32)
+    end_ref = np.zeros(shape, dtype=np.int32)
+    mat = np.ascontiguousarray(mat, dtype=np.int32)
+    mapper = np.ascontiguousarray(mapper, dtype=np.uint8)
+    _ffi.check(lib.qcb_sg_batch(default_device() if device is None else int(device),
+                                _vp(qbuf), _vp(qoff), len(queries), _vp(rbuf), _vp(roff), len(refs),
+                                int(open), int(extend), _vp(mat), msize, _vp(mapper),
+                                _vp(score), _vp(end_query), _vp(end_ref)))
+    return score, end_query, end_ref
+
+
+class DevicePlan(object):
+    """Immutable device-side copy of a scanner's tables plus its workspace."""
+
+    def __init__(self, tables, device=None):
+        if not isinstance(tables, Tables):
+            raise TypeError("tables must be a qcat_b200.tables.Tables")
+        self._lib = _ffi.load()
+        self.tables = tables
+        self.device = default_device() if device is None else int(device)
+        struct, self._keep = _ffi.tables_struct(tables)
+        self._handle = self._lib.qcb_plan_create(ctypes.byref(struct), self.device)
+        if not self._handle:
+            raise _ffi.QcbError(_ffi.last_error() or "qcb_plan_create failed")
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.qcb_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        out = _ffi.QcbPlanInfo()
+        _ffi.check(self._lib.qcb_plan_info(self._handle, ctypes.byref(out)))
+        return {name: getattr(out, name) for name, _ in out._fields_}
+
+    def set_force_generic(self, force):
+        _ffi.check(self._lib.qcb_plan_set_force_generic(self._handle, 1 if force else 0))
+
+    @staticmethod
+    def _subset(subset):
+        if subset is None:
+            return None, 0
+        arr = np.ascontiguousarray(subset, dtype=np.int32)
+        return arr, int(arr.size)
+
+    # ---- host buffers ---------------------------------------------------------------------------
+
+    def detect(self, win5, tail3, wlen, read_len, subset=None, out=None):
+        """qcb_detect on host numpy arrays (see tables.pack_windows) -> structured array (RESULT_DTYPE)."""
+        win5 = np.ascontiguousarray(win5, dtype=np.uint8)
+        tail3 = np.ascontiguousarray(tail3, dtype=np.uint8)
+        wlen = np.ascontiguousarray(wlen, dtype=np.int32)
+        read_len = np.ascontiguousarray(read_len, dtype=np.int64)
+        n = int(wlen.shape[0])
+        stride = int(win5.shape[1]) if win5.ndim == 2 else int(win5.size // max(n, 1))
+        if out is None:
+            out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+        sub, nsub = self._subset(subset)
+        _ffi.check(self._lib.qcb_detect(self._handle, _vp(win5), _vp(tail3), stride, _vp(wlen), _vp(read_len), n,
+                                        _vp(sub) if sub is not None else None, nsub, _vp(out)))
+        return out
+
+    def detect_reads(self, read_sequences, subset=None):
+        win5, tail3, wlen, read_len, _ = pack_windows(read_sequences, self.tables.max_align_length)
+        return self.detect(win5, tail3, wlen, read_len, subset)
+
+    def scan_windows(self, windows, subset=None):
+        """qcb_scan on a list of already-oriented window strings of any length -> structured array."""
+        raw = [w if isinstance(w, bytes) else (w or "").encode("latin-1", "replace") for w in windows]
+        n = len(raw)
+        longest = max([len(r) for r in raw] + [1])
+        stride = (longest + 15) // 16 * 16
+        buf = np.zeros((n, stride), dtype=np.uint8)
+        wlen = np.zeros(n, dtype=np.int32)
+        for i, r in enumerate(raw):
+            wlen[i] = len(r)
+            buf[i, :len(r)] = np.frombuffer(r, dtype=np.uint8)
+        out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+        sub, nsub = self._subset(subset)
+        _ffi.check(self._lib.qcb_scan(self._handle, _vp(buf), stride, _vp(wlen), n,
+                                      _vp(sub) if sub is not None else None, nsub, _vp(out)))
+        return out
+
+    def kit_vote(self, win5, tail3, wlen):
+        win5 = np.ascontiguousarray(win5, dtype=np.uint8)
+        tail3 = np.ascontiguousarray(tail3, dtype=np.uint8)
+        wlen = np.ascontiguousarray(wlen, dtype=np.int32)
+        n = int(wlen.shape[0])
+        stride = int(win5.shape[1])
+        vote = np.zeros(n, dtype=np.int32)
+        _ffi.check(self._lib.qcb_kit_vote(self._handle, _vp(win5), _vp(tail3), stride, _vp(wlen), n, _vp(vote)))
+        return vote
+
+    # ---- device buffers (raw pointers) ----------------------------------------------------------
+
+    def detect_device(self, d_win5, d_tail3, stride, d_wlen, d_read_len, n_reads, d_out, subset=None, stream=0):
+        sub, nsub = self._subset(subset)
+        _ffi.check(self._lib.qcb_detect_device(self._handle, ctypes.c_void_p(d_win5), ctypes.c_void_p(d_tail3), int(stride),
+                                               ctypes.c_void_p(d_wlen), ctypes.c_void_p(d_read_len), int(n_reads),
+                                               _vp(sub) if sub is not None else None, nsub,
+                                               ctypes.c_void_p(d_out), ctypes.c_void_p(stream)))
+
+    def kit_vote_device(self, d_win5, d_tail3, stride, d_wlen, n_reads, d_vote, stream=0):
+        _ffi.check(self._lib.qcb_kit_vote_device(self._handle, ctypes.c_void_p(d_win5), ctypes.c_void_p(d_tail3), int(stride),
+                                                 ctypes.c_void_p(d_wlen), int(n_reads), ctypes.c_void_p(d_vote),
+                                                 ctypes.c_void_p(stream)))
+
+    def histogram_device(self, d_results, n_reads, layout_bin_base, d_counts, n_bins, stream=0):
+        base = np.ascontiguousarray(layout_bin_base, dtype=np.int32)
+        _ffi.check(self._lib.qcb_histogram_device(self._handle, ctypes.c_void_p(d_results), int(n_reads), _vp(base),
+                                                  ctypes.c_void_p(d_counts), int(n_bins), ctypes.c_void_p(stream)))
+
+    def histogram_layout(self):
+        """(layout_bin_base, n_bins): bin 0 = unclassified, then one bin per (layout, barcode index)."""
+        t = self.tables
+        base = np.zeros(t.n_layouts, dtype=np.int32)
+        total = 0
+        for i in range(t.n_layouts):
+            base[i] = total
+            size = t.group_size(i, 0)
+            if t.mode == 1:
+                size *= t.group_size(i, 1)
+            total += size
+        return base, total + 1
+
+
+def microbench_cell_rate(device=None):
+    """(packed DP cell updates per second the SMs can issue, effective SM MHz) on this device."""
+    cells = ctypes.c_double()
+    mhz = ctypes.c_double()
+    _ffi.check(_ffi.load().qcb_microbench_cell_rate(default_device() if device is None else int(device),
+                                                    ctypes.byref(cells), ctypes.byref(mhz)))
+    return cells.value, mhz.value

@@ -1,0 +1,125 @@
+"""Test-side access to the CPU oracle (oracle/, TEST INFRASTRUCTURE ONLY) and the golden vectors."""
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import build as oracle_build  # noqa: E402
+sys.path.pop(0)
+
+from qcat_b200 import _ffi, config, scanner  # noqa: E402
+from qcat_b200.tables import Tables  # noqa: E402
+
+RESULT_FIELDS = ("layout", "barcode", "barcode_score", "adapter_end", "trim5p", "trim3p", "exit_status")
+
+_oracle = None
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        lib = ctypes.CDLL(oracle_build.build())
+        for name in ("qo_sg", "qo_detect", "qo_kit_vote", "qo_find_best_adapter_template"):
+            getattr(lib, name).restype = None
+        lib.qo_count_cells.restype = ctypes.c_int64
+        _oracle = lib
+    return _oracle
+
+
+def _vp(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def oracle_detect(tables, win5, tail3, wlen, read_len, subset=None, threads=None):
+    """qo_detect (oracle/qcat_oracle.c) on packed windows -> structured array."""
+    lib = oracle_lib()
+    st, keep = _ffi.tables_struct(tables)          # qo_tables has the same field layout as qcb_tables
+    n = int(len(wlen))
+    out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+    win5 = np.ascontiguousarray(win5, dtype=np.uint8)
+    tail3 = np.ascontiguousarray(tail3, dtype=np.uint8)
+    wlen = np.ascontiguousarray(wlen, dtype=np.int32)
+    read_len = np.ascontiguousarray(read_len, dtype=np.int64)
+    sub = None if subset is None else np.ascontiguousarray(subset, dtype=np.int32)
+    lib.qo_detect(ctypes.byref(st), _vp(win5), _vp(tail3), ctypes.c_int(win5.shape[1]), _vp(wlen), _vp(read_len),
+                  ctypes.c_int64(n), _vp(sub), ctypes.c_int(0 if sub is None else sub.size), _vp(out),
+                  ctypes.c_int(threads or os.cpu_count() or 1))
+    return out
+
+
+def oracle_kit_vote(tables, win5, tail3, wlen, threads=None):
+    lib = oracle_lib()
+    st, keep = _ffi.tables_struct(tables)
+    n = int(len(wlen))
+    vote = np.zeros(n, dtype=np.int32)
+    win5 = np.ascontiguousarray(win5, dtype=np.uint8)
+    tail3 = np.ascontiguousarray(tail3, dtype=np.uint8)
+    wlen = np.ascontiguousarray(wlen, dtype=np.int32)
+    lib.qo_kit_vote(ctypes.byref(st), _vp(win5), _vp(tail3), ctypes.c_int(win5.shape[1]), _vp(wlen), ctypes.c_int64(n),
+                    _vp(vote), ctypes.c_int(threads or os.cpu_count() or 1))
+    return vote
+
+
+def oracle_count_cells(tables, win5, tail3, wlen, subset=None):
+    lib = oracle_lib()
+    st, keep = _ffi.tables_struct(tables)
+    n = int(len(wlen))
+    sub = np.arange(tables.n_layouts, dtype=np.int32) if subset is None else np.ascontiguousarray(subset, dtype=np.int32)
+    full = ctypes.c_int64(0)
+    cells = lib.qo_count_cells(ctypes.byref(st), _vp(np.ascontiguousarray(win5)), _vp(np.ascontiguousarray(tail3)),
+                               ctypes.c_int(win5.shape[1]), _vp(np.ascontiguousarray(wlen, dtype=np.int32)),
+                               ctypes.c_int64(n), _vp(sub), ctypes.c_int(sub.size), ctypes.byref(full))
+    return int(cells), int(full.value)
+
+
+def oracle_sg(query, ref, open, extend, matrix):
+    lib = oracle_lib()
+    size, mat, mapper = config.matrix_arrays(matrix)
+    q = query if isinstance(query, bytes) else query.encode("latin-1", "replace")
+    r = ref if isinstance(ref, bytes) else ref.encode("latin-1", "replace")
+    sc, eq, er = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    mat = np.ascontiguousarray(mat, dtype=np.int32)
+    mapper = np.ascontiguousarray(mapper, dtype=np.uint8)
+    lib.qo_sg(q, len(q), r, len(r), int(open), int(extend), _vp(mat), size, _vp(mapper),
+              ctypes.byref(sc), ctypes.byref(eq), ctypes.byref(er))
+    return sc.value, eq.value, er.value
+
+
+def load_golden():
+    data = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+    meta = json.loads(bytes(data["cases"]).decode())
+    return data, meta["cases"], meta["ranges"]
+
+
+def scanner_for_case(case, device=None):
+    cls = scanner.BarcodeScannerDual if case["mode"] == "dual" else scanner.BarcodeScannerEPI2ME
+    sc = cls(min_quality=case["min_quality"], kit=case["kit"], device=device)
+    assert [l.kit for l in sc.layouts] == case["layout_kits"], "layout order differs from the golden run"
+    return sc
+
+
+def tables_for_case(case):
+    sc = scanner_for_case(case)
+    return Tables(sc.layouts, config.qcatConfig(), case["mode"], sc.min_quality), sc
+
+
+def kit_from_votes(vote, names):
+    return scanner.GpuScannerMixin._kit_from_votes(vote, names)
+
+
+def assert_records_equal(got, want, what=""):
+    for f in RESULT_FIELDS:
+        a, b = got[f], want[f]
+        if f == "barcode_score":
+            same = a.view(np.int64) == b.view(np.int64)          # bit-exact doubles
+        else:
+            same = a == b
+        if not same.all():
+            bad = np.nonzero(~same)[0]
+            i = int(bad[0])
+            raise AssertionError("%s: field %s differs on %d/%d records; first at %d: got %r want %r" %
+                                 (what, f, bad.size, len(want), i, got[i], want[i]))
