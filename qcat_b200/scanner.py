@@ -91,7 +91,7 @@ class GpuScannerMixin(object):
             result["exit_status"] = int(rec["exit_status"])
         else:
             barcode = plan.tables.barcode_object(layout_index, int(rec["barcode"]))
-            if isinstance(barcode, tuple):      # dual: synthesised pair (scanner_dual.py:132-136)
+            if plan.tables.mode == 1:           # dual: synthesised pair (scanner_dual.py:132-136)
                 first, second = barcode
                 barcode = Barcode("barcode{:02d}/{:02d}".format(first.id, second.id),
                                   "{}/{}".format(first.id, second.id), None, True)
