@@ -104,6 +104,14 @@ int       qcb_plan_info(qcb_plan *plan, qcb_plan_info_t *out);
 /* 0 = automatic (fast kernels when the scoring scheme allows), 1 = force the generic kernels. */
 int       qcb_plan_set_force_generic(qcb_plan *plan, int force);
 
+/* Per-stage device timing (CUDA events around each pipeline stage on the launching stream).  Off by default.
+ * Stages: 0 orient (window extraction + revcomp), 1 adapter DP, 2 template selection / region geometry,
+ * 3 barcode DP, 4 two-end decision (or kit vote).  qcb_plan_stage_times synchronises the recorded events,
+ * adds the elapsed milliseconds of every launch since the last reset into ms[5] / launches[5]. */
+#define QCB_N_STAGES 5
+int       qcb_plan_set_profiling(qcb_plan *plan, int enable);
+int       qcb_plan_stage_times(qcb_plan *plan, double *ms, int64_t *launches, int reset);
+
 /* Batched semi-global alignment, every query against every reference: out[q * n_refs + r].
  * Replaces parasail.sg_striped_32 (scanner_base.py:111-117, 214-218).  Host buffers. */
 int qcb_sg_batch(int device,

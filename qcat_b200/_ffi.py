@@ -96,7 +96,7 @@ def tables_struct(tables):
 
 # Every symbol include/qcat_b200.h declares (tests check the library exports all of them).
 EXPORTS = ("qcb_device_count", "qcb_last_error", "qcb_version", "qcb_plan_create", "qcb_plan_destroy", "qcb_plan_info",
-           "qcb_plan_set_force_generic", "qcb_sg_batch", "qcb_scan", "qcb_detect", "qcb_detect_device", "qcb_kit_vote",
+           "qcb_plan_set_force_generic", "qcb_plan_set_profiling", "qcb_plan_stage_times", "qcb_sg_batch", "qcb_scan", "qcb_detect", "qcb_detect_device", "qcb_kit_vote",
            "qcb_kit_vote_device", "qcb_histogram_device", "qcb_microbench_cell_rate")
 
 _lib = None
@@ -126,6 +126,10 @@ def load():
     lib.qcb_plan_info.argtypes = [vp, ctypes.POINTER(QcbPlanInfo)]
     lib.qcb_plan_set_force_generic.restype = ctypes.c_int
     lib.qcb_plan_set_force_generic.argtypes = [vp, ctypes.c_int]
+    lib.qcb_plan_set_profiling.restype = ctypes.c_int
+    lib.qcb_plan_set_profiling.argtypes = [vp, ctypes.c_int]
+    lib.qcb_plan_stage_times.restype = ctypes.c_int
+    lib.qcb_plan_stage_times.argtypes = [vp, vp, vp, ctypes.c_int]
     lib.qcb_sg_batch.restype = ctypes.c_int
     lib.qcb_sg_batch.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, ctypes.c_int32,
                                  ctypes.c_int32, vp, ctypes.c_int32, vp, vp, vp, vp]

@@ -71,6 +71,11 @@ struct qcb_plan {
     DeviceBuffer wins, ad_score, ad_end, sel, bc_score, subset_dev, in_stage, out_stage, misc;
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
     long long launches = 0;
+    bool profiling = false;
+    struct StageEvent { int stage; cudaEvent_t a, b; long long launches; };
+    std::vector<StageEvent> stage_events;
+    double stage_ms[QCB_N_STAGES] = {0, 0, 0, 0, 0};
+    long long stage_launches[QCB_N_STAGES] = {0, 0, 0, 0, 0};
     long long chunk_reads = 1 << 18;
 };
 
@@ -171,6 +176,22 @@ int validate_tables(const qcb_tables *h)
 }
 
 // Run the pipeline over one chunk of reads already resident on the device.
+struct StageTimer {
+    qcb_plan *p; int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; long long l0;
+    StageTimer(qcb_plan *p_, int stage_, cudaStream_t st_) : p(p_), stage(stage_), st(st_), l0(p_->launches)
+    {
+        if (!p->profiling) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+    }
+    ~StageTimer()
+    {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        p->stage_events.push_back({stage, a, b, p->launches - l0});
+    }
+};
+
 // d_tail3 == nullptr selects window mode: d_win5 holds n already-oriented windows (BarcodeScanner.scan).
 int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int stride, const int32_t *d_wlen,
               const int64_t *d_read_len, long long n, const int32_t *d_subset, const int32_t *h_subset, int n_subset,
@@ -187,12 +208,15 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
     const uint8_t *wins = d_win5;
     int32_t *ad_score = (int32_t *)p->ad_score.ptr, *ad_end = (int32_t *)p->ad_end.ptr;
     if (!window_mode) {
+        StageTimer timer(p, 0, st);
         k_orient<<<grid_for(nw * stride, 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, (uint8_t *)p->wins.ptr);
         p->launches++;
         wins = (const uint8_t *)p->wins.ptr;
     }
 
     const bool fast_ok = !p->force_generic && !window_mode && stride <= kFastMaxStride;
+    {
+    StageTimer timer(p, 1, st);
     if (fast_ok && p->fast.adapter_ok) {
         int rc = fast_adapter_stage(p->fast, t, wins, stride, d_wlen, nw, d_subset, h_subset, n_subset, ad_score, ad_end, st,
                                     &p->launches);
@@ -202,7 +226,9 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
                                                                        ad_score, ad_end);
         p->launches++;
     }
+    }
     if (d_vote) {
+        StageTimer timer(p, 4, st);
         k_kit_vote<<<grid_for(n, 256), 256, 0, st>>>(t, d_wlen, n, d_subset, n_subset, ad_score, ad_end, d_vote);
         p->launches++;
         QCB_CUDA(cudaGetLastError());
@@ -212,8 +238,13 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
     if (p->bc_score.reserve((size_t)nw * bslots * 4)) return 1;
     WindowSel *sel = (WindowSel *)p->sel.ptr;
     int32_t *bc_score = (int32_t *)p->bc_score.ptr;
+    {
+    StageTimer timer(p, 2, st);
     k_select<<<grid_for(nw, 256), 256, 0, st>>>(t, d_wlen, wshift, nw, d_subset, n_subset, ad_score, ad_end, sel);
     p->launches++;
+    }
+    {
+    StageTimer timer(p, 3, st);
     if (fast_ok && p->fast.barcode_ok) {
         int rc = fast_barcode_stage(p->fast, t, wins, stride, nw, sel, p->bmax0, bslots, bc_score, st, &p->launches);
         if (rc) return fail("fast barcode stage launch failed");
@@ -221,6 +252,8 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
         k_barcode_generic<<<grid_for(nw * bslots, 128), 128, 0, st>>>(t, wins, stride, nw, sel, p->bmax0, bslots, bc_score);
         p->launches++;
     }
+    }
+    StageTimer timer(p, 4, st);
     if (window_mode) k_scan_out<<<grid_for(nw, 128), 128, 0, st>>>(t, d_wlen, nw, sel, bc_score, p->bmax0, bslots, d_out);
     else k_finalize<<<grid_for(n, 128), 128, 0, st>>>(t, d_wlen, d_read_len, n, sel, bc_score, p->bmax0, bslots, d_out);
     p->launches++;
@@ -368,6 +401,34 @@ int qcb_plan_set_force_generic(qcb_plan *p, int force)
 {
     if (!p) return fail("plan is NULL");
     p->force_generic = force != 0;
+    return 0;
+}
+
+int qcb_plan_set_profiling(qcb_plan *p, int enable)
+{
+    if (!p) return fail("plan is NULL");
+    p->profiling = enable != 0;
+    return 0;
+}
+
+int qcb_plan_stage_times(qcb_plan *p, double *ms, int64_t *launches, int reset)
+{
+    if (!p) return fail("plan is NULL");
+    QCB_CUDA(cudaSetDevice(p->device));
+    for (auto &ev : p->stage_events) {
+        QCB_CUDA(cudaEventSynchronize(ev.b));
+        float t = 0.f;
+        QCB_CUDA(cudaEventElapsedTime(&t, ev.a, ev.b));
+        p->stage_ms[ev.stage] += t;
+        p->stage_launches[ev.stage] += ev.launches;
+        cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+    }
+    p->stage_events.clear();
+    for (int i = 0; i < QCB_N_STAGES; ++i) {
+        if (ms) ms[i] = p->stage_ms[i];
+        if (launches) launches[i] = p->stage_launches[i];
+        if (reset) { p->stage_ms[i] = 0; p->stage_launches[i] = 0; }
+    }
     return 0;
 }
 

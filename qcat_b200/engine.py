@@ -90,6 +90,18 @@ class DevicePlan(object):
     def set_force_generic(self, force):
         _ffi.check(self._lib.qcb_plan_set_force_generic(self._handle, 1 if force else 0))
 
+    STAGES = ("orient", "adapter", "select", "barcode", "decide")
+
+    def set_profiling(self, enable):
+        _ffi.check(self._lib.qcb_plan_set_profiling(self._handle, 1 if enable else 0))
+
+    def stage_times(self, reset=True):
+        """{stage: (milliseconds, kernel launches)} accumulated since the last reset (synchronises)."""
+        ms = np.zeros(len(self.STAGES), dtype=np.float64)
+        launches = np.zeros(len(self.STAGES), dtype=np.int64)
+        _ffi.check(self._lib.qcb_plan_stage_times(self._handle, _vp(ms), _vp(launches), 1 if reset else 0))
+        return {name: (float(ms[i]), int(launches[i])) for i, name in enumerate(self.STAGES)}
+
     @staticmethod
     def _subset(subset):
         if subset is None:
