@@ -68,7 +68,7 @@ struct qcb_plan {
     int max_adapter = 0, max_template = 0;
     FastPlan fast;                   // packed-kernel tables (kernels_fast.cuh)
     // workspace, sized per chunk of reads
-    DeviceBuffer wins, ad_score, ad_end, sel, bc_score, subset_dev, in_stage, out_stage, misc;
+    DeviceBuffer wins, codes, ad_score, ad_end, sel, bc_score, subset_dev, in_stage, out_stage, misc;
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
     long long launches = 0;
     bool profiling = false;
@@ -207,21 +207,30 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
     if (p->ad_end.reserve((size_t)nw * n_subset * 4)) return 1;
     const uint8_t *wins = d_win5;
     int32_t *ad_score = (int32_t *)p->ad_score.ptr, *ad_end = (int32_t *)p->ad_end.ptr;
+    const bool fast_ok = !p->force_generic && !window_mode && stride <= kFastMaxStride && (stride % 16) == 0 &&
+                         (p->fast.adapter_ok || p->fast.barcode_ok);
     if (!window_mode) {
         StageTimer timer(p, 0, st);
-        k_orient<<<grid_for(nw * stride, 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, (uint8_t *)p->wins.ptr);
+        if (fast_ok) {
+            if (p->codes.reserve((size_t)nw * stride)) return 1;
+            k_orient_codes<<<grid_for(nw * (stride / 4), 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, t.amap, t.bmap,
+                                                                          (uint8_t *)p->wins.ptr, (uint8_t *)p->codes.ptr);
+        } else {
+            k_orient<<<grid_for(nw * stride, 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, (uint8_t *)p->wins.ptr);
+        }
         p->launches++;
         wins = (const uint8_t *)p->wins.ptr;
     }
 
-    const bool fast_ok = !p->force_generic && !window_mode && stride <= kFastMaxStride;
     {
     StageTimer timer(p, 1, st);
+    int adapter_rc = 2;
     if (fast_ok && p->fast.adapter_ok) {
-        int rc = fast_adapter_stage(p->fast, t, wins, stride, d_wlen, nw, d_subset, h_subset, n_subset, ad_score, ad_end, st,
-                                    &p->launches);
-        if (rc) return fail("fast adapter stage launch failed");
-    } else {
+        adapter_rc = fast_adapter_stage(p->fast, t, (const uint8_t *)p->codes.ptr, stride, d_wlen, wshift, nw, h_subset, n_subset,
+                                        ad_score, ad_end, st, &p->launches);
+        if (adapter_rc == 1) return fail("fast adapter stage launch failed");
+    }
+    if (adapter_rc == 2) {
         k_adapter_generic<<<grid_for(nw * n_subset, 128), 128, 0, st>>>(t, wins, stride, d_wlen, wshift, nw, d_subset, n_subset,
                                                                        ad_score, ad_end);
         p->launches++;
@@ -376,7 +385,7 @@ void qcb_plan_destroy(qcb_plan *p)
     if (!p) return;
     cudaSetDevice(p->device);
     fast_plan_free(p->fast);
-    p->wins.release(); p->ad_score.release(); p->ad_end.release(); p->sel.release(); p->bc_score.release();
+    p->wins.release(); p->codes.release(); p->ad_score.release(); p->ad_end.release(); p->sel.release(); p->bc_score.release();
     p->subset_dev.release(); p->in_stage.release(); p->out_stage.release(); p->misc.release();
     if (p->slab) cudaFree(p->slab);
     if (p->stream) cudaStreamDestroy(p->stream);

@@ -52,6 +52,15 @@ struct FastDev {
     int32_t n_groups;
 };
 
+struct AdapterSubset {       // packed adapter profile for one layout subset (pairs of consecutive subset entries)
+    std::vector<int32_t> key;
+    void *dev = nullptr;      // profile words followed by int4 pair meta
+    size_t bytes = 0;
+    int npairs = 0, nc_cols = 0, row_words = 0;
+    size_t profile_bytes = 0;
+    std::vector<uint8_t> host;   // staging copy (kept alive for the async upload)
+};
+
 struct FastPlan {
     bool adapter_ok = false;
     bool barcode_ok = false;
@@ -61,7 +70,18 @@ struct FastPlan {
     size_t slab_bytes = 0;
     int sm_count = 0;
     size_t barcode_smem = 0;
-    size_t workspace_bytes() const { return slab_bytes; }
+    // adapter stage: host copies used to build per-subset profiles
+    int a_gap = 0, a_codes = 0;
+    std::vector<int32_t> a_mat;
+    std::vector<uint8_t> a_map;
+    std::vector<std::vector<uint8_t>> a_seq;       // per layout adapter sequence (ASCII)
+    std::vector<AdapterSubset *> subsets;
+    size_t workspace_bytes() const
+    {
+        size_t b = slab_bytes;
+        for (auto *sub : subsets) b += sub->bytes;
+        return b;
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -225,6 +245,145 @@ k_barcode_fast(FastDev f, DevTables t, const uint8_t *__restrict__ wins, int str
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Adapter stage.  One lane = one window x two adapter templates (u16 halves); a warp = 32 windows x one
+// template pair; the whole template lives in NC registers, right-aligned (dead columns in front keep the
+// left border value i*g, so the last register is always the last template column).  Per row the last
+// column feeds a (value, first row) key; at row n the last row is scanned for (value, first column) and the
+// parasail end-cell rule is applied (see sg_affine in kernels_generic.cuh / qo_sg in the oracle).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kAdapterWarps = 4;
+
+template <int NC>
+__global__ void __launch_bounds__(kAdapterWarps * 32, (NC <= 48 ? 6 : (NC <= 64 ? 5 : 3)))
+k_adapter_fast(const uint32_t *__restrict__ profile, int profile_words, int row_words, int n_codes,
+               const int4 *__restrict__ pair_meta, int npairs,
+               const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ wlen, int wshift,
+               long long n_windows, int n_subset, int g, int32_t *__restrict__ ad_score, int32_t *__restrict__ ad_end)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *s_prof = (uint32_t *)smem;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint8_t *s_code = smem + (size_t)profile_words * 4 + (size_t)warp * (kRows * kTile);
+    for (int i = threadIdx.x; i < profile_words; i += blockDim.x) s_prof[i] = profile[i];
+    __syncthreads();
+
+    const long long n_tiles = (n_windows + kTile - 1) / kTile;
+    const long long n_tasks = n_tiles * npairs;
+    const long long warp_stride = (long long)gridDim.x * kAdapterWarps;
+    for (long long task = (long long)blockIdx.x * kAdapterWarps + warp; task < n_tasks; task += warp_stride) {
+        const long long tile = task / npairs;
+        const int q = (int)(task % npairs);
+        const int4 meta = pair_meta[q];                 // x = len lo, y = len hi, z = has hi
+        const int m_lo = meta.x, m_hi = meta.y;
+        const long long w = tile * kTile + lane;
+        const bool valid = w < n_windows;
+        const int n = valid ? wlen[w >> wshift] : 0;
+        // ---- stage the lane's window codes (low nibble = adapter-matrix code) into shared memory ----
+        __syncwarp();
+        {
+            const uint4 *src = (const uint4 *)(codes + (valid ? w : 0) * stride);
+            for (int ch = 0; ch * 16 < n; ++ch) {
+                uint4 v = src[ch];
+                uint32_t words[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int b = 0; b < 16; ++b)
+                    s_code[(ch * 16 + b + 1) * kTile + lane] = (uint8_t)((words[b >> 2] >> ((b & 3) * 8)) & 15u);
+            }
+        }
+        __syncwarp();
+        const int nmax = __reduce_max_sync(0xffffffffu, n);
+        const uint32_t *pbase = s_prof + (size_t)q * n_codes * row_words;
+        uint32_t Wc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            int jl = c - (NC - m_lo) + 1, jh = c - (NC - m_hi) + 1;
+            Wc[c] = (uint32_t)(max(jl, 0) * g) | ((uint32_t)(max(jh, 0) * g) << 16);
+        }
+        const uint32_t gdup = dup16((uint32_t)g);
+        uint32_t border = 0;                            // (i - 1) * g in both halves
+        int best_lo = 0, best_hi = 0;                   // ((W - i g) << 8) | (255 - i), max over rows
+        for (int i = 1; i <= nmax; ++i) {
+            const int code = (i <= n) ? s_code[i * kTile + lane] : 0;
+            const uint4 *prow = (const uint4 *)(pbase + code * row_words);
+            uint32_t diag = border;
+            border += gdup;
+            uint32_t left = border;
+#pragma unroll
+            for (int c = 0; c < NC; c += 4) {
+                const uint4 e = prow[c >> 2];
+                uint32_t tt;
+                tt = diag + e.x; diag = Wc[c];     left = __vimax3_u16x2(tt, diag, left); Wc[c] = left;
+                tt = diag + e.y; diag = Wc[c + 1]; left = __vimax3_u16x2(tt, diag, left); Wc[c + 1] = left;
+                tt = diag + e.z; diag = Wc[c + 2]; left = __vimax3_u16x2(tt, diag, left); Wc[c + 2] = left;
+                tt = diag + e.w; diag = Wc[c + 3]; left = __vimax3_u16x2(tt, diag, left); Wc[c + 3] = left;
+            }
+            if (i <= n) {
+                const int rowc = (255 - i) - ((i * g) << 8);
+                best_lo = max(best_lo, (int)(left & 0xffffu) * 256 + rowc);
+                best_hi = max(best_hi, (int)(left >> 16) * 256 + rowc);
+            }
+            if (__any_sync(0xffffffffu, i == n)) {
+                if (i == n) {
+                    int rb_lo = -1, rb_hi = -1;         // ((W - j g) << 8) | (255 - j), max over real columns
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const int jl = c - (NC - m_lo) + 1, jh = c - (NC - m_hi) + 1;
+                        if (jl >= 1) rb_lo = max(rb_lo, ((int)(Wc[c] & 0xffffu) - jl * g) * 256 + (255 - jl));
+                        if (jh >= 1) rb_hi = max(rb_hi, ((int)(Wc[c] >> 16) - jh * g) * 256 + (255 - jh));
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 1 && !meta.z) break;
+                        const int m = h ? m_hi : m_lo;
+                        const int best = h ? best_hi : best_lo, rb = h ? rb_hi : rb_lo;
+                        const int C = (best >> 8) - m * g, iC = 255 - (best & 255);
+                        const int R = (rb >> 8) - n * g, jR = 255 - (rb & 255);
+                        int score, end;
+                        if (C > R) { score = C; end = iC - 1; }
+                        else { score = R; end = n - 1; if (jR == m) end = iC - 1; }
+                        const long long o = w * n_subset + 2 * q + h;
+                        ad_score[o] = score;
+                        ad_end[o] = end;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Window orientation for the packed kernels: ASCII windows (as k_orient) plus one byte per base holding both
+// matrix codes (low nibble adapter matrix, high nibble barcode matrix).
+__global__ void k_orient_codes(const uint8_t *__restrict__ win5, const uint8_t *__restrict__ tail3, int stride,
+                               const int32_t *__restrict__ wlen, long long n_reads, const uint8_t *__restrict__ comp,
+                               const uint8_t *__restrict__ amap, const uint8_t *__restrict__ bmap,
+                               uint8_t *__restrict__ wins, uint8_t *__restrict__ codes)
+{
+    __shared__ uint8_t s_comp[256], s_pack[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_comp[i] = comp[i]; s_pack[i] = (uint8_t)(amap[i] | (bmap[i] << 4)); }
+    __syncthreads();
+    long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per 4 bases
+    const int quads = stride >> 2;
+    if (id >= n_reads * 2 * quads) return;
+    long long w = id / quads;
+    int i0 = (int)(id % quads) * 4;
+    long long r = w >> 1;
+    int len = wlen[r];
+    uint32_t a = 0, c = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        int i = i0 + b;
+        uint8_t v = 0;
+        if (i < len) v = (w & 1) ? s_comp[tail3[r * stride + (len - 1 - i)]] : win5[r * stride + i];
+        a |= (uint32_t)v << (8 * b);
+        c |= (uint32_t)(i < len ? s_pack[v] : 0) << (8 * b);
+    }
+    ((uint32_t *)wins)[id] = a;
+    ((uint32_t *)codes)[id] = c;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side: build the packed-kernel tables
 // ---------------------------------------------------------------------------------------------------
@@ -233,12 +392,40 @@ inline void fast_plan_free(FastPlan &fp)
 {
     if (fp.slab) cudaFree(fp.slab);
     fp.slab = nullptr; fp.slab_bytes = 0;
+    for (auto *sub : fp.subsets) { if (sub->dev) cudaFree(sub->dev); delete sub; }
+    fp.subsets.clear();
+}
+
+inline void fast_adapter_prepare(FastPlan &fp, const qcb_tables *h)
+{
+    fp.adapter_ok = false;
+    const int g = h->adapter_open, nc = h->amat_size;
+    if (h->adapter_open != h->adapter_extend || g <= 0) return;
+    if (h->max_align_length > kFastMaxStride) return;
+    int smax = 0, mlen = 0;
+    for (int i = 0; i < nc * nc; ++i) {
+        if (h->amat[i] + 2 * g < 0) return;
+        smax = std::max(smax, h->amat[i]);
+    }
+    fp.a_seq.clear();
+    for (int L = 0; L < h->n_layouts; ++L) {
+        int len = h->adapter_off[L + 1] - h->adapter_off[L];
+        if (len < 1 || len > 104) return;
+        mlen = std::max(mlen, len);
+        fp.a_seq.emplace_back(h->adapter_seq + h->adapter_off[L], h->adapter_seq + h->adapter_off[L + 1]);
+    }
+    if (smax * mlen + (kFastMaxStride + mlen) * g + 64 >= 32768) return;
+    if (255 - kFastMaxStride < 0 || mlen > 250) return;
+    fp.a_gap = g; fp.a_codes = nc;
+    fp.a_mat.assign(h->amat, h->amat + nc * nc);
+    fp.a_map.assign(h->amap, h->amap + 256);
+    fp.adapter_ok = true;
 }
 
 inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
 {
     fp.sm_count = sm_count;
-    fp.adapter_ok = false;
+    fast_adapter_prepare(fp, h);
     fp.barcode_ok = false;
     const int g = h->barcode_open;
     const int nc = h->bmat_size;
@@ -360,10 +547,81 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     return 0;
 }
 
-inline int fast_adapter_stage(FastPlan &, const DevTables &, const uint8_t *, int, const int32_t *, long long,
-                              const int32_t *, const int32_t *, int, int32_t *, int32_t *, cudaStream_t, long long *)
+inline AdapterSubset *adapter_subset(FastPlan &fp, const int32_t *h_subset, int n_subset, cudaStream_t st)
 {
-    return 1;
+    std::vector<int32_t> key(h_subset, h_subset + n_subset);
+    for (auto *sub : fp.subsets)
+        if (sub->key == key) return sub;
+    AdapterSubset *sub = new AdapterSubset();
+    sub->key = key;
+    int mlen = 0;
+    for (int v : key) mlen = std::max(mlen, (int)fp.a_seq[v].size());
+    const int NC = mlen <= 48 ? 48 : (mlen <= 64 ? 64 : 104);
+    const int row_words = NC + 4, nc = fp.a_codes, g = fp.a_gap;
+    const int npairs = (n_subset + 1) / 2;
+    sub->npairs = npairs; sub->nc_cols = NC; sub->row_words = row_words;
+    sub->profile_bytes = (size_t)npairs * nc * row_words * 4;
+    sub->host.assign(sub->profile_bytes + (size_t)npairs * 16, 0);
+    uint32_t *prof = (uint32_t *)sub->host.data();
+    int32_t *meta = (int32_t *)(sub->host.data() + sub->profile_bytes);
+    for (int q = 0; q < npairs; ++q) {
+        const std::vector<uint8_t> &A = fp.a_seq[key[2 * q]];
+        const bool has_hi = 2 * q + 1 < n_subset;
+        const std::vector<uint8_t> &B = fp.a_seq[key[has_hi ? 2 * q + 1 : 2 * q]];
+        meta[q * 4 + 0] = (int)A.size(); meta[q * 4 + 1] = (int)B.size(); meta[q * 4 + 2] = has_hi ? 1 : 0;
+        for (int code = 0; code < nc; ++code)
+            for (int c = 0; c < NC; ++c) {
+                int ja = c - (NC - (int)A.size()), jb = c - (NC - (int)B.size());
+                uint32_t lo = ja >= 0 ? (uint32_t)(fp.a_mat[code * nc + fp.a_map[A[ja]]] + 2 * g) : 0u;
+                uint32_t hi = jb >= 0 ? (uint32_t)(fp.a_mat[code * nc + fp.a_map[B[jb]]] + 2 * g) : 0u;
+                prof[((size_t)q * nc + code) * row_words + c] = lo | (hi << 16);
+            }
+    }
+    sub->bytes = sub->host.size();
+    if (cudaMalloc(&sub->dev, sub->bytes) != cudaSuccess) { delete sub; return nullptr; }
+    if (cudaMemcpyAsync(sub->dev, sub->host.data(), sub->bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        cudaFree(sub->dev); delete sub; return nullptr;
+    }
+    fp.subsets.push_back(sub);
+    return sub;
+}
+
+template <int NC>
+inline int launch_adapter_fast(FastPlan &fp, AdapterSubset *sub, const uint8_t *codes, int stride, const int32_t *wlen, int wshift,
+                               long long n_windows, int n_subset, int32_t *ad_score, int32_t *ad_end, cudaStream_t st)
+{
+    const size_t smem = sub->profile_bytes + (size_t)kAdapterWarps * kRows * kTile;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(k_adapter_fast<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+        configured = smem;
+    }
+    const long long n_tiles = (n_windows + kTile - 1) / kTile;
+    const long long n_tasks = n_tiles * sub->npairs;
+    int per_sm = NC <= 48 ? 6 : (NC <= 64 ? 5 : 3);
+    while (per_sm > 1 && per_sm * smem > 200 * 1024) --per_sm;
+    const int grid = (int)std::min<long long>((n_tasks + kAdapterWarps - 1) / kAdapterWarps, (long long)fp.sm_count * per_sm);
+    if (grid <= 0) return 0;
+    k_adapter_fast<NC><<<grid, kAdapterWarps * 32, smem, st>>>((const uint32_t *)sub->dev, (int)(sub->profile_bytes / 4), sub->row_words,
+                                                             fp.a_codes, (const int4 *)((const uint8_t *)sub->dev + sub->profile_bytes),
+                                                             sub->npairs, codes, stride, wlen, wshift, n_windows, n_subset, fp.a_gap,
+                                                             ad_score, ad_end);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+inline int fast_adapter_stage(FastPlan &fp, const DevTables &, const uint8_t *codes, int stride, const int32_t *wlen, int wshift,
+                              long long n_windows, const int32_t *h_subset, int n_subset, int32_t *ad_score, int32_t *ad_end,
+                              cudaStream_t st, long long *launches)
+{
+    AdapterSubset *sub = adapter_subset(fp, h_subset, n_subset, st);
+    if (!sub) return 1;
+    if (sub->profile_bytes + (size_t)kAdapterWarps * kRows * kTile > 200 * 1024) return 2;    // caller falls back
+    int rc;
+    if (sub->nc_cols == 48) rc = launch_adapter_fast<48>(fp, sub, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
+    else if (sub->nc_cols == 64) rc = launch_adapter_fast<64>(fp, sub, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
+    else rc = launch_adapter_fast<104>(fp, sub, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
+    if (rc == 0) ++*launches;
+    return rc;
 }
 
 inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, const uint8_t *wins, int stride, long long n_windows,
