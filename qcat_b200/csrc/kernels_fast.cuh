@@ -213,12 +213,15 @@ k_barcode_fast(FastDev f, DevTables t, const uint8_t *__restrict__ wins, int str
                 }
                 const uint32_t Fi = dup16(s_F[i * kTile + lane]);
                 const uint32_t Gi = dup16(s_G[i * kTile + lane]);
-                uint32_t diag = Fprev, left = Fi;
+                // two passes so every register is updated in place (no rotation copies): first all diagonal terms
+                // from the previous row's values, then the left-to-right max chain.
+                e[0] += Fprev;
+#pragma unroll
+                for (int c = 1; c < kCore; ++c) e[c] += Wc[c - 1];
+                uint32_t left = Fi;
 #pragma unroll
                 for (int c = 0; c < kCore; ++c) {
-                    uint32_t tt = diag + e[c];
-                    diag = Wc[c];
-                    left = __vimax3_u16x2(tt, diag, left);
+                    left = __vimax3_u16x2(e[c], Wc[c], left);
                     Wc[c] = left;
                 }
                 Fprev = Fi;
@@ -308,17 +311,22 @@ k_adapter_fast(const uint32_t *__restrict__ profile, int profile_words, int row_
         for (int i = 1; i <= nmax; ++i) {
             const int code = (i <= n) ? s_code[i * kTile + lane] : 0;
             const uint4 *prow = (const uint4 *)(pbase + code * row_words);
-            uint32_t diag = border;
+            // diagonal terms are formed from the previous row's registers one 4-column chunk ahead of the max chain,
+            // so every Wc register is updated in place (no rotation copies).
+            uint4 e = prow[0];
+            uint32_t t0 = border + e.x;
             border += gdup;
             uint32_t left = border;
 #pragma unroll
             for (int c = 0; c < NC; c += 4) {
-                const uint4 e = prow[c >> 2];
-                uint32_t tt;
-                tt = diag + e.x; diag = Wc[c];     left = __vimax3_u16x2(tt, diag, left); Wc[c] = left;
-                tt = diag + e.y; diag = Wc[c + 1]; left = __vimax3_u16x2(tt, diag, left); Wc[c + 1] = left;
-                tt = diag + e.z; diag = Wc[c + 2]; left = __vimax3_u16x2(tt, diag, left); Wc[c + 2] = left;
-                tt = diag + e.w; diag = Wc[c + 3]; left = __vimax3_u16x2(tt, diag, left); Wc[c + 3] = left;
+                uint4 en = make_uint4(0, 0, 0, 0);
+                if (c + 4 < NC) en = prow[(c >> 2) + 1];
+                const uint32_t t1 = Wc[c] + e.y, t2 = Wc[c + 1] + e.z, t3 = Wc[c + 2] + e.w, t0n = Wc[c + 3] + en.x;
+                left = __vimax3_u16x2(t0, Wc[c], left);     Wc[c] = left;
+                left = __vimax3_u16x2(t1, Wc[c + 1], left); Wc[c + 1] = left;
+                left = __vimax3_u16x2(t2, Wc[c + 2], left); Wc[c + 2] = left;
+                left = __vimax3_u16x2(t3, Wc[c + 3], left); Wc[c + 3] = left;
+                t0 = t0n; e = en;
             }
             if (i <= n) {
                 const int rowc = (255 - i) - ((i * g) << 8);
