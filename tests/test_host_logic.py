@@ -1,0 +1,157 @@
+"""CPU: host-side mirrors (config, layout, kit loading, window packing, vote rule) behave like the reference's."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import refloader  # noqa: E402
+sys.path.pop(0)
+
+needs_reference = pytest.mark.skipif(not refloader.available(), reason="reference package not available")
+
+
+def test_get_placeholder_pos():
+    """Same cases as the reference's test_get_placeholder (test_barcode.py:15-67)."""
+    from qcat_b200.layout import AdapterLayout
+    pos = AdapterLayout.get_placeholder_pos
+    assert tuple(pos("NNNNN")) == (0, 4, 5)
+    assert tuple(pos("AAAANNNNN")) == (4, 8, 5)
+    assert tuple(pos("NNNNNAAAA")) == (0, 4, 5)
+    assert tuple(pos("")) == (-1, -1, 0)
+    assert tuple(pos("AATGTACTTCGTT")) == (-1, -1, 0)
+    two = "AATGTACTTCGTTCAGTTACGTATTGCT" + "N" * 24 + "GTTTTCGCATTTATCGTG" + "N" * 10 + "AAACGC"
+    assert tuple(pos(two, 0)) == (28, 51, 24)
+    assert tuple(pos(two, 1)) == (70, 79, 10)
+
+
+def test_scoring_matrices_match_the_reference_values():
+    """Adapter matrix over ATGCNX with the N / X rows poked as in config.py:236-253; barcode matrix +-1."""
+    from qcat_b200 import config
+    cfg = config.qcatConfig()
+    size, mat, mapper = config.matrix_arrays(cfg.matrix)
+    m = mat.reshape(size, size)
+    assert size == 7
+    assert [m[i, i] for i in range(4)] == [5] * 4 and m[0, 1] == -2
+    assert list(m[4, :5]) == [-1] * 5 and list(m[:4, 4]) == [-1] * 4          # N row / column
+    assert list(m[5]) == [0] * 7 and list(m[:, 5]) == [0] * 7                  # X row / column
+    assert list(m[6]) == [0] * 7                                               # wildcard
+    assert mapper[ord("a")] == mapper[ord("A")] == 0 and mapper[ord("t")] == 1 and mapper[ord("?")] == 6
+    size_b, mat_b, map_b = config.matrix_arrays(cfg.matrix_barcode)
+    mb = mat_b.reshape(size_b, size_b)
+    assert size_b == 6 and mb[4, 4] == 1 and mb[0, 4] == -1 and list(mb[5]) == [0] * 6
+    cfg.match = -7            # setters normalise the sign like the reference (config.py:49-57)
+    cfg.mismatch = 3
+    assert cfg.match == 7 and cfg.mismatch == -3
+    assert config.matrix_arrays(cfg.matrix)[1].reshape(7, 7)[1, 1] == 7
+
+
+@needs_reference
+def test_config_and_layout_mirrors_equal_the_reference_objects():
+    refloader.load()
+    from qcat import adapters as ref_adapters
+    from qcat import config as ref_config
+    from qcat_b200 import adapters, config
+    a = config.matrix_arrays(config.qcatConfig().matrix)
+    b = config.matrix_arrays(ref_config.qcatConfig().matrix)
+    assert a[0] == b[0] and (a[1] == b[1]).all() and (a[2] == b[2]).all()
+    a = config.matrix_arrays(config.qcatConfig().matrix_barcode)
+    b = config.matrix_arrays(ref_config.qcatConfig().matrix_barcode)
+    assert a[0] == b[0] and (a[1] == b[1]).all() and (a[2] == b[2]).all()
+    mine = {(l.kit, l.sequence): l for l in adapters.populate_adapter_layouts()}
+    for ref in ref_adapters.populate_adapter_layouts():
+        l = mine[(ref.kit, ref.sequence)]
+        for k in (0, 1):
+            assert l.get_barcode_end(k) == ref.get_barcode_end(k)
+            assert l.get_barcode_length(k) == ref.get_barcode_length(k)
+            assert l.get_upstream_context(11, k) == ref.get_upstream_context(11, k)
+            assert l.get_downstream_context(11, k) == ref.get_downstream_context(11, k)
+        assert l.is_double_barcode() == ref.is_double_barcode() and l.trim_offset == ref.trim_offset
+        assert l.get_adapter_length() == ref.get_adapter_length() and l.auto_detect == ref.auto_detect
+
+
+def test_kit_selection_and_factory():
+    from qcat_b200 import scanner
+    assert len(scanner.BarcodeScannerEPI2ME().layouts) == 12                     # auto_detect layouts
+    assert len(scanner.BarcodeScannerEPI2ME(kit="Auto").layouts) == 12
+    assert [l.kit for l in scanner.BarcodeScannerEPI2ME(kit="pbc096").layouts] == ["PBC096", "PBC096"]
+    assert scanner.BarcodeScannerEPI2ME(kit="nonexistent").layouts == []
+    assert scanner.factory(mode="dual").min_quality == 60 and scanner.factory().min_quality == 58
+    assert scanner.factory(mode="guppy").get_name() == "epi2me"
+    assert sorted(scanner.get_modes()) == ["dual", "epi2me"]
+    assert "PBC096" in scanner.get_kits() and scanner.get_kits()[0] == "Auto"
+    with pytest.raises(RuntimeError):
+        scanner.factory(mode="simple")
+
+
+def test_pack_windows_is_extract_align_sequence():
+    """win5 = read[:W], tail3 = read[-W:] (scanner_base.py:223-244), ragged and empty reads included."""
+    from qcat_b200.tables import pack_windows
+    from qcat_b200.scanner import revcomp
+    reads = ["", None, "ACG", "A" * 150, "ACGT" * 100, "acgtRYN-" * 30]
+    win5, tail3, wlen, read_len, stride = pack_windows(reads, 150)
+    assert stride == 160 and win5.shape == (6, 160)
+    for i, r in enumerate(reads):
+        r = r or ""
+        assert read_len[i] == len(r) and wlen[i] == min(len(r), 150)
+        assert bytes(win5[i, :wlen[i]]).decode() == r[:150]
+        assert bytes(tail3[i, :wlen[i]]).decode() == r[-150:]
+    assert revcomp("ACGTNacgtRYKMx") == "xKMRYacgtNACGT"
+
+
+def test_kit_vote_tie_rule():
+    """Most abundant kit, first seen wins ties (dict order + stable sort, scanner_base.py:645-660)."""
+    names = ["A", "B", "B", "C"]
+    vote = np.array([3, 1, 0, 2, 3, 0], dtype=np.int32)       # C, B, A, B, C, A -> all 2: first seen is C
+    assert helpers.kit_from_votes(vote, names) == "C"
+    assert helpers.kit_from_votes(np.array([1, 2, 0], dtype=np.int32), names) == "B"
+    assert helpers.kit_from_votes(np.array([], dtype=np.int32), names) is None
+
+
+def test_filter_barcodes_and_counts():
+    from qcat_b200 import scanner
+    from qcat_b200.adapters import Barcode
+    sc = scanner.BarcodeScannerEPI2ME(kit="PBC096", enable_filter_barcodes=True)
+    b1, b2 = Barcode("barcode01", 1, "A", True), Barcode("barcode02", 2, "C", True)
+    results = [scanner.build_return_dict(b1, 90.0, sc.layouts[0], 50, 0) for _ in range(100)]
+    results += [scanner.build_return_dict(b2, 90.0, sc.layouts[0], 50, 0) for _ in range(5)]
+    results += [scanner.empty_return_dict()]
+    counts = {}
+    for r in results:
+        sc.update_barcode_count(r, counts)
+    assert counts == {1: 100, 2: 5, "0": 1}
+    out = sc.filter_barcodes(counts, list(results))
+    assert sum(1 for r in out if r["barcode"] is b1) == 100
+    assert all(r["barcode"] is None for r in out[100:])       # 5 <= int(100 * 0.05): dropped
+
+
+def test_synthetic_generator_is_deterministic_and_well_formed():
+    from qcat_b200 import scanner, synth
+    sc = scanner.BarcodeScannerEPI2ME(kit="PBC096")
+    a = synth.generate(sc.layouts, 500, seed=3)
+    b = synth.generate(sc.layouts, 500, seed=3)
+    for k in ("win5", "tail3", "wlen", "read_len", "truth_barcode"):
+        assert (a[k] == b[k]).all()
+    assert a["win5"].shape == (500, 160) and (a["wlen"] == 150).all() and (a["read_len"] >= 300).all()
+    assert set(np.unique(a["win5"][:, :150])) <= set(b"ACGTN")
+    assert (a["win5"][:, 150:] == 0).all()
+    reads = synth.windows_to_reads(a, range(5))
+    assert [len(r) for r in reads] == list(a["read_len"][:5])
+
+
+def test_oracle_counts_reference_cells():
+    """Algorithmic DP cells per read for PBC096 on un-barcoded windows = 35 700 + 1 209 600."""
+    from qcat_b200 import config, scanner
+    from qcat_b200.tables import Tables
+    sc = scanner.BarcodeScannerEPI2ME(kit="PBC096")
+    tables = Tables(sc.layouts, config.qcatConfig(), "epi2me", sc.min_quality)
+    rng = np.random.default_rng(1)
+    win = np.zeros((50, 160), dtype=np.uint8)
+    win[:, :150] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(50, 150))]
+    wlen = np.full(50, 150, dtype=np.int32)
+    cells, full = helpers.oracle_count_cells(tables, win, win, wlen)
+    assert full == 100 and cells == 50 * (35700 + 1209600)
