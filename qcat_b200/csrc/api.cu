@@ -255,7 +255,7 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
     {
     StageTimer timer(p, 3, st);
     if (fast_ok && p->fast.barcode_ok) {
-        int rc = fast_barcode_stage(p->fast, t, wins, stride, nw, sel, p->bmax0, bslots, bc_score, st, &p->launches);
+        int rc = fast_barcode_stage(p->fast, t, (const uint8_t *)p->codes.ptr, stride, nw, sel, p->bmax0, bslots, bc_score, st, &p->launches);
         if (rc) return fail("fast barcode stage launch failed");
     } else {
         k_barcode_generic<<<grid_for(nw * bslots, 128), 128, 0, st>>>(t, wins, stride, nw, sel, p->bmax0, bslots, bc_score);

@@ -1,0 +1,190 @@
+// Barcode stage, packed kernels (included from kernels_fast.cuh; structs FastDev / FastGroup live there).
+//
+//   k_context       per (window, set) task: the two shared-context columns F and G and the base codes of the region,
+//                   packed one u32 per DP row:  code (4 bits) | F (14 bits) | G (14 bits), W space.
+//   k_barcode_fast  lane = window x two barcodes, profile from shared memory (any set size).
+// (textually included inside namespace qcb by kernels_fast.cuh)
+
+constexpr int kRowTile = 32;                       // tasks per row-info tile
+
+__device__ __forceinline__ long long rowinfo_base(long long task)
+{
+    return (task >> 5) * (long long)(kRows * kRowTile) + (task & 31);
+}
+
+// Task order: epi2me t = window; dual t = k * n_windows + w (all first-set tasks, then all second-set tasks).
+__device__ __forceinline__ void decode_task(long long t, long long n_windows, int dual, long long &w, int &k)
+{
+    if (dual && t >= n_windows) { w = t - n_windows; k = 1; } else { w = t; k = 0; }
+}
+
+// Shared-context columns.  F[i] = H[i][u] + (i+u) g for the forward DP of region rows vs the shared prefix;
+// G[i] = H'[n-i][d] + (n-i+d) g for the DP of the reversed region vs the reversed shared suffix, whose left border
+// is 0 except -g at its last row (node (0, m) is not a valid end).  See DESIGN.md section 4.
+__global__ void __launch_bounds__(128)
+k_context(FastDev f, DevTables t, const uint8_t *__restrict__ codes, int stride, long long n_windows,
+          const WindowSel *__restrict__ sel, int dual, uint32_t *__restrict__ rowinfo, int4 *__restrict__ taskmeta)
+{
+    __shared__ int32_t s_sp[kMaxMatrix * kMaxMatrix];
+    for (int i = threadIdx.x; i < f.n_codes * f.n_codes; i += blockDim.x) s_sp[i] = f.sprime[i] - 2 * f.gap;   // plain M
+    __syncthreads();
+    const long long n_tasks = dual ? 2 * n_windows : n_windows;
+    const long long task = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (task >= n_tasks) return;
+    long long w; int k;
+    decode_task(task, n_windows, dual, w, k);
+    const WindowSel s = sel[w];
+    const int lo = k ? s.lo1 : s.lo0, hi = k ? s.hi1 : s.hi0;
+    const int grp = t.group[s.layout * 2 + k];
+    int n = hi - lo;
+    if (grp < 0 || n < 0) n = 0;
+    const FastGroup G = f.groups[grp < 0 ? 0 : grp];
+    const int g = f.gap, nc = f.n_codes;
+    const uint8_t *src = codes + w * stride + lo;
+    uint32_t *out = rowinfo + rowinfo_base(task);
+
+    int H[kMaxCtx + 1];
+    int cc[kMaxCtx];
+    // ---- forward: shared prefix ----
+    const int u = G.u, d = G.d;
+#pragma unroll
+    for (int j = 0; j <= kMaxCtx; ++j) H[j] = 0;
+#pragma unroll
+    for (int j = 0; j < kMaxCtx; ++j) cc[j] = j < u ? f.ctx_codes[G.up_off + j] : 0;
+    out[0] = (uint32_t)(u * g) << 4;
+    for (int i = 1; i <= n; ++i) {
+        const int code = src[i - 1] >> 4;
+        const int32_t *sp = s_sp + code * nc;
+        int diag = 0, left = 0;
+#pragma unroll
+        for (int j = 1; j <= kMaxCtx; ++j) {
+            if (j <= u) {
+                const int up = H[j];
+                const int h = max(max(diag + sp[cc[j - 1]], up - g), left - g);
+                diag = up; H[j] = h; left = h;
+            }
+        }
+        out[(long long)i * kRowTile] = (uint32_t)code | ((uint32_t)(left + (i + u) * g) << 4);
+    }
+    int rup = INT32_MIN / 2;
+#pragma unroll
+    for (int j = 1; j <= kMaxCtx; ++j)
+        if (j <= u) rup = max(rup, H[j]);
+    // ---- backward: shared suffix (reversed region vs reversed suffix) ----
+#pragma unroll
+    for (int j = 0; j <= kMaxCtx; ++j) H[j] = 0;
+#pragma unroll
+    for (int j = 0; j < kMaxCtx; ++j) cc[j] = j < d ? f.ctx_codes[G.down_off + d - 1 - j] : 0;
+    out[(long long)n * kRowTile] |= (uint32_t)(d * g) << 18;
+    for (int i = 1; i <= n; ++i) {
+        const int code = src[n - i] >> 4;
+        const int32_t *sp = s_sp + code * nc;
+        int diag = 0;
+        int left = (i == n) ? -g : 0;
+#pragma unroll
+        for (int j = 1; j <= kMaxCtx; ++j) {
+            if (j <= d) {
+                const int up = H[j];
+                const int h = max(max(diag + sp[cc[j - 1]], up - g), left - g);
+                diag = up; H[j] = h; left = h;
+            }
+        }
+        out[(long long)(n - i) * kRowTile] |= (uint32_t)(left + (i + d) * g) << 18;
+    }
+    taskmeta[task] = make_int4(n, grp, rup, 0);
+}
+
+// Result of one (window, barcode pair): score = max(R over prefix columns, R over core columns, join with G).
+__device__ __forceinline__ void store_pair_scores(const uint32_t (&Wc)[kCore], uint32_t acc, const FastGroup &G, int n, int g, int rup,
+                                                  int pr, int32_t *dst)
+{
+    const int CB = (G.u + kCore) * g;
+    uint32_t rm = 0;
+#pragma unroll
+    for (int c = 0; c < kCore - 1; ++c)
+        rm = __viaddmax_u16x2(Wc[c], dup16((uint32_t)(CB - (G.u + max(0, c + 1 - G.pad)) * g)), rm);
+    const int bias_r = n * g + CB, bias_j = (n + G.tlen) * g;
+    const int s0 = max(max((int)(rm & 0xffffu) - bias_r, (int)(acc & 0xffffu) - bias_j), rup);
+    const int s1 = max(max((int)(rm >> 16) - bias_r, (int)(acc >> 16) - bias_j), rup);
+    dst[2 * pr] = s0;
+    if (2 * pr + 1 < G.nb) dst[2 * pr + 1] = s1;
+}
+
+// Lane = window x two barcodes (u16 halves); warp = 32 windows x one barcode pair; profile rows via multicast LDS.
+__global__ void __launch_bounds__(kBarcodeWarps * 32, 3)
+k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots,
+               const uint32_t *__restrict__ rowinfo, const int4 *__restrict__ taskmeta, int32_t *__restrict__ bc_score)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *s_prof = (uint32_t *)smem;
+    uint32_t *s_row = (uint32_t *)(smem + f.profile_bytes);          // [kRows][32]: code | F << 4 | G << 18
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < f.profile_bytes / 4; i += blockDim.x) s_prof[i] = f.profile[i];
+
+    const long long n_tasks = dual ? 2 * n_windows : n_windows;
+    const long long n_tiles = (n_tasks + kRowTile - 1) / kRowTile;
+    const int g = f.gap;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();                       // previous tile fully consumed (and the profile copy above is complete)
+        const long long task = tile * kRowTile + lane;
+        int4 meta = make_int4(0, 0, 0, 0);
+        if (task < n_tasks) meta = taskmeta[task];
+        const FastGroup G = f.groups[meta.y < 0 ? 0 : meta.y];
+        int n = meta.y < 0 ? 0 : meta.x;
+        const int nmax = __reduce_max_sync(0xffffffffu, n);
+        if (__syncthreads_or(nmax > 0) == 0) continue;               // tile has nothing for this kernel
+        {
+            const uint32_t *src = rowinfo + tile * (long long)(kRows * kRowTile);
+            const int words = (nmax + 1) * kRowTile;
+            for (int i = threadIdx.x; i < words; i += blockDim.x) s_row[i] = src[i];
+        }
+        __syncthreads();
+        long long w; int k;
+        decode_task(task < n_tasks ? task : 0, n_windows, dual, w, k);
+        const int rup = meta.z;
+        const int npairs = (G.nb + 1) >> 1;
+        const int npairs_max = __reduce_max_sync(0xffffffffu, n > 0 ? npairs : 0);
+        const int v = G.u + (kCore - G.pad);            // last core column (template coordinates)
+        int32_t *dst = bc_score + w * bslots + (k ? bmax0 : 0);
+        for (int pr = warp; pr < npairs_max; pr += kBarcodeWarps) {
+            const int pcl = min(pr, npairs - 1);
+            const uint8_t *prow = (const uint8_t *)s_prof + G.prof_off + pcl * (f.n_codes * kProfWords * 4);
+            uint32_t Wc[kCore];
+#pragma unroll
+            for (int c = 0; c < kCore; ++c) Wc[c] = dup16((uint32_t)((G.u + max(0, c + 1 - G.pad)) * g));
+            const uint32_t info0 = s_row[lane];
+            uint32_t Fprev = dup16((info0 >> 4) & 0x3fffu);
+            uint32_t acc = dup16((uint32_t)(v * g)) + dup16(info0 >> 18);          // join term of row 0
+            for (int i = 1; i <= nmax; ++i) {
+                const uint32_t info = s_row[i * kRowTile + lane];
+                const uint4 *prow_i = (const uint4 *)(prow + (info & 15u) * (kProfWords * 4));
+                uint32_t e[kCore];
+#pragma unroll
+                for (int c = 0; c < kCore; c += 4) {
+                    const uint4 q = prow_i[c >> 2];
+                    e[c] = q.x; e[c + 1] = q.y; e[c + 2] = q.z; e[c + 3] = q.w;
+                }
+                const uint32_t Fi = dup16((info >> 4) & 0x3fffu);
+                const uint32_t Gi = dup16(info >> 18);
+                // diagonal terms first (previous row's registers), then the in-place left-to-right max chain
+                e[0] += Fprev;
+#pragma unroll
+                for (int c = 1; c < kCore; ++c) e[c] += Wc[c - 1];
+                uint32_t left = Fi;
+#pragma unroll
+                for (int c = 0; c < kCore; ++c) {
+                    left = __vimax3_u16x2(e[c], Wc[c], left);
+                    Wc[c] = left;
+                }
+                Fprev = Fi;
+                if (i <= n) acc = __viaddmax_u16x2(left, Gi, acc);
+                if (__any_sync(0xffffffffu, i == n)) {
+                    if (i == n && pr < npairs) store_pair_scores(Wc, acc, G, n, g, rup, pr, dst);
+                }
+            }
+        }
+    }
+}

@@ -70,6 +70,9 @@ struct FastPlan {
     size_t slab_bytes = 0;
     int sm_count = 0;
     size_t barcode_smem = 0;
+    void *rowinfo = nullptr;         // [tiles][kRows][32] u32: code | F << 4 | G << 18
+    void *taskmeta = nullptr;        // [tasks] int4 {region length, group, R over prefix columns, -}
+    size_t rowinfo_bytes = 0, taskmeta_bytes = 0;
     // adapter stage: host copies used to build per-subset profiles
     int a_gap = 0, a_codes = 0;
     std::vector<int32_t> a_mat;
@@ -78,7 +81,7 @@ struct FastPlan {
     std::vector<AdapterSubset *> subsets;
     size_t workspace_bytes() const
     {
-        size_t b = slab_bytes;
+        size_t b = slab_bytes + rowinfo_bytes + taskmeta_bytes;
         for (auto *sub : subsets) b += sub->bytes;
         return b;
     }
@@ -90,164 +93,7 @@ struct FastPlan {
 
 __device__ __forceinline__ uint32_t dup16(uint32_t v) { return v * 0x00010001u; }
 
-// Last column of the semi-global DP (zero borders, H space, linear gap g) of `n` region rows against `len`
-// context columns, for every row: out[pos(i)] = H[i][len] + (i + len) g   (W space, >= 0).
-// reverse = false: rows i = 1..n read region code i, columns read ctx[0..len), pos(i) = i            (column F)
-// reverse = true : rows i' = 1..n read region code n - i' + 1, columns read ctx[len-1..0], the left border of
-//                  row n is -g instead of 0 and pos(i') = n - i'                                      (column G)
-// Returns max_{1<=j<=len} H[n][j] of the forward problem (INT_MIN/2 when len == 0).
-__device__ __forceinline__ int context_column(const uint8_t *s_code, int lane, int n, const uint8_t *ctx, int len,
-                                              const int32_t *s_sp, int n_codes, int g, bool reverse, uint16_t *s_out)
-{
-    int H[kMaxCtx + 1];
-#pragma unroll
-    for (int j = 0; j <= kMaxCtx; ++j) H[j] = 0;
-    int cc[kMaxCtx];
-#pragma unroll
-    for (int j = 0; j < kMaxCtx; ++j) cc[j] = j < len ? ctx[reverse ? len - 1 - j : j] : 0;
-    s_out[(reverse ? n : 0) * kTile + lane] = (uint16_t)(len * g);          // row 0: H = 0
-    for (int i = 1; i <= n; ++i) {
-        int code = s_code[(reverse ? n - i + 1 : i) * kTile + lane];
-        const int32_t *sp = s_sp + code * n_codes;
-        int diag = 0;
-        int left = (reverse && i == n) ? -g : 0;
-        H[0] = left;
-#pragma unroll
-        for (int j = 1; j <= kMaxCtx; ++j) {
-            if (j <= len) {
-                int up = H[j];
-                int h = max(max(diag + sp[cc[j - 1]] - 2 * g, up - g), left - g);
-                diag = up; H[j] = h; left = h;
-            }
-        }
-        int last = len > 0 ? left : H[0];
-        s_out[(reverse ? n - i : i) * kTile + lane] = (uint16_t)(last + (i + len) * g);
-    }
-    int rmax = INT32_MIN / 2;
-#pragma unroll
-    for (int j = 1; j <= kMaxCtx; ++j)
-        if (j <= len) rmax = max(rmax, H[j]);
-    return rmax;
-}
-
-// Barcode stage.  Persistent CTAs; each iteration takes one tile of 32 window tasks.  Task t = window (epi2me) or
-// (window, set) (dual: t = 2 w + k).  Output: bc_score[w * bslots + (k ? bmax0 : 0) + b] for every barcode b.
-__global__ void __launch_bounds__(kBarcodeWarps * 32, 3)
-k_barcode_fast(FastDev f, DevTables t, const uint8_t *__restrict__ wins, int stride, long long n_windows,
-               const WindowSel *__restrict__ sel, int dual, int bmax0, int bslots, int32_t *__restrict__ bc_score)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint32_t *s_prof = (uint32_t *)smem;
-    uint8_t *p = smem + f.profile_bytes;
-    uint16_t *s_off = (uint16_t *)p;  p += kRows * kTile * 2;      // profile row byte offset of the row's base code
-    uint16_t *s_F = (uint16_t *)p;    p += kRows * kTile * 2;      // F column (W space)
-    uint16_t *s_G = (uint16_t *)p;    p += kRows * kTile * 2;      // G column (W space)
-    uint8_t *s_code = p;              p += kRows * kTile;          // barcode-matrix code of region row i
-    int32_t *s_sp = (int32_t *)p;     p += kMaxMatrix * kMaxMatrix * 4;
-    int32_t *s_rup = (int32_t *)p;    p += kTile * 4;
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < f.profile_bytes / 4; i += blockDim.x) s_prof[i] = f.profile[i];
-    for (int i = threadIdx.x; i < f.n_codes * f.n_codes; i += blockDim.x) s_sp[i] = f.sprime[i];
-
-    const long long n_tasks = dual ? 2 * n_windows : n_windows;
-    const long long n_tiles = (n_tasks + kTile - 1) / kTile;
-    const int g = f.gap;
-
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        __syncthreads();                       // previous tile fully consumed (also covers the table loads above)
-        // ---- per-lane task description (every warp computes the same values for its lane) ----
-        long long task = tile * kTile + lane;
-        bool valid = task < n_tasks;
-        long long w = valid ? (dual ? task >> 1 : task) : 0;
-        int k = (valid && dual) ? (int)(task & 1) : 0;
-        WindowSel s = sel[w];
-        int lo = k ? s.lo1 : s.lo0, hi = k ? s.hi1 : s.hi0;
-        int n = valid ? hi - lo : 0;
-        int grp = t.group[s.layout * 2 + k];
-        FastGroup G = f.groups[grp < 0 ? 0 : grp];
-        if (grp < 0) n = 0;
-
-        // ---- phase 0: region codes -> shared memory (thread x handles rows x/32, x/32 + 8, ... of its lane) ----
-        {
-            const uint8_t *src = wins + w * stride + lo;
-            for (int i = warp; i < kRows; i += kBarcodeWarps) {
-                int code = 0;
-                if (i >= 1 && i <= n) code = t.bmap[src[i - 1]];
-                s_code[i * kTile + lane] = (uint8_t)code;
-                s_off[i * kTile + lane] = (uint16_t)(code * (kProfWords * 4));
-            }
-        }
-        __syncthreads();
-        // ---- phase 1: shared-prefix column F (warp 0) and shared-suffix column G (warp 1) ----
-        if (warp == 0) {
-            int rup = context_column(s_code, lane, n, f.ctx_codes + G.up_off, G.u, s_sp, f.n_codes, g, false, s_F);
-            s_rup[lane] = rup;
-        } else if (warp == 1) {
-            context_column(s_code, lane, n, f.ctx_codes + G.down_off, G.d, s_sp, f.n_codes, g, true, s_G);
-        }
-        __syncthreads();
-
-        // ---- phase 2: core columns, one barcode pair per warp iteration ----
-        const int nmax = __reduce_max_sync(0xffffffffu, n);
-        const int npairs = (G.nb + 1) >> 1;
-        const int npairs_max = __reduce_max_sync(0xffffffffu, n > 0 ? npairs : 0);
-        const int m = G.tlen;
-        const int v = G.u + (kCore - G.pad);            // last core column (template coordinates)
-        for (int pr = warp; pr < npairs_max; pr += kBarcodeWarps) {
-            const int pcl = min(pr, npairs - 1);
-            const uint8_t *prow = (const uint8_t *)s_prof + G.prof_off + pcl * (f.n_codes * kProfWords * 4);
-            uint32_t Wc[kCore];
-#pragma unroll
-            for (int c = 0; c < kCore; ++c) Wc[c] = dup16((uint32_t)((G.u + max(0, c + 1 - G.pad)) * g));
-            uint32_t Fprev = dup16(s_F[lane]);
-            uint32_t acc = dup16((uint32_t)(v * g)) + dup16(s_G[lane]);          // join term of row 0
-            for (int i = 1; i <= nmax; ++i) {
-                const uint4 *prow_i = (const uint4 *)(prow + s_off[i * kTile + lane]);
-                uint32_t e[kCore];
-#pragma unroll
-                for (int c = 0; c < kCore; c += 4) {
-                    uint4 q = prow_i[c >> 2];
-                    e[c] = q.x; e[c + 1] = q.y; e[c + 2] = q.z; e[c + 3] = q.w;
-                }
-                const uint32_t Fi = dup16(s_F[i * kTile + lane]);
-                const uint32_t Gi = dup16(s_G[i * kTile + lane]);
-                // two passes so every register is updated in place (no rotation copies): first all diagonal terms
-                // from the previous row's values, then the left-to-right max chain.
-                e[0] += Fprev;
-#pragma unroll
-                for (int c = 1; c < kCore; ++c) e[c] += Wc[c - 1];
-                uint32_t left = Fi;
-#pragma unroll
-                for (int c = 0; c < kCore; ++c) {
-                    left = __vimax3_u16x2(e[c], Wc[c], left);
-                    Wc[c] = left;
-                }
-                Fprev = Fi;
-                if (i <= n) acc = __viaddmax_u16x2(left, Gi, acc);
-                if (__any_sync(0xffffffffu, i == n)) {
-                    if (i == n && pr < npairs) {
-                        // last row over the core columns: max_c (W[n][col_c] - (n + col_c) g), col_c = u + max(0, c+1-pad)
-                        const int CB = (G.u + kCore) * g;
-                        uint32_t rm = 0;
-#pragma unroll
-                        for (int c = 0; c < kCore - 1; ++c)
-                            rm = __viaddmax_u16x2(Wc[c], dup16((uint32_t)(CB - (G.u + max(0, c + 1 - G.pad)) * g)), rm);
-                        const int rup = s_rup[lane];
-                        const int bias_r = n * g + CB, bias_j = (n + m) * g;
-                        int s0 = max(max((int)(rm & 0xffffu) - bias_r, (int)(acc & 0xffffu) - bias_j), rup);
-                        int s1 = max(max((int)(rm >> 16) - bias_r, (int)(acc >> 16) - bias_j), rup);
-                        int32_t *dst = bc_score + w * bslots + (k ? bmax0 : 0) + 2 * pr;
-                        dst[0] = s0;
-                        if (2 * pr + 1 < G.nb) dst[1] = s1;
-                    }
-                }
-            }
-        }
-    }
-}
-
+#include "kernels_barcode_fast.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // Adapter stage.  One lane = one window x two adapter templates (u16 halves); a warp = 32 windows x one
@@ -400,6 +246,9 @@ inline void fast_plan_free(FastPlan &fp)
 {
     if (fp.slab) cudaFree(fp.slab);
     fp.slab = nullptr; fp.slab_bytes = 0;
+    if (fp.rowinfo) cudaFree(fp.rowinfo);
+    if (fp.taskmeta) cudaFree(fp.taskmeta);
+    fp.rowinfo = fp.taskmeta = nullptr; fp.rowinfo_bytes = fp.taskmeta_bytes = 0;
     for (auto *sub : fp.subsets) { if (sub->dev) cudaFree(sub->dev); delete sub; }
     fp.subsets.clear();
 }
@@ -477,7 +326,7 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
         int core = tlen - u - d;
         while (core > kCore && u < kMaxCtx && nb == 1) { ++u; --core; }
         if (core < 1 || core > kCore) return 0;
-        if ((smax * tlen + (kFastMaxStride + tlen) * g) * 2 + 64 >= 65536) return 0;
+        if (smax * tlen + (kFastMaxStride + tlen) * g + 64 >= 16384) return 0;      // F / G are packed into 14 bits
         G.ok = 1; G.u = u; G.d = d; G.pad = kCore - core; G.tlen = tlen; G.nb = nb;
         G.up_off = (int32_t)ctx.size();
         for (int j = 0; j < u; ++j) ctx.push_back(h->bmap[first[j]]);
@@ -545,7 +394,7 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     fp.dev.n_codes = nc;
     fp.dev.gap = g;
     fp.dev.n_groups = ng;
-    fp.barcode_smem = profile_bytes + (size_t)kRows * kTile * (2 + 2 + 2 + 1) + kMaxMatrix * kMaxMatrix * 4 + kTile * 4;
+    fp.barcode_smem = profile_bytes + (size_t)kRows * kRowTile * 4;
     if (fp.barcode_smem > 220 * 1024) return 0;
     if (cudaFuncSetAttribute(k_barcode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.barcode_smem) != cudaSuccess) {
         cudaGetLastError();
@@ -632,19 +481,37 @@ inline int fast_adapter_stage(FastPlan &fp, const DevTables &, const uint8_t *co
     return rc;
 }
 
-inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, const uint8_t *wins, int stride, long long n_windows,
+inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, const uint8_t *codes, int stride, long long n_windows,
                               const WindowSel *sel, int bmax0, int bslots, int32_t *bc_score, cudaStream_t st,
                               long long *launches)
 {
     const int dual = t.mode == QCB_MODE_DUAL ? 1 : 0;
-    long long n_tasks = dual ? 2 * n_windows : n_windows;
-    long long n_tiles = (n_tasks + kTile - 1) / kTile;
-    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (220 * 1024) / std::max<size_t>(1, fp.barcode_smem)));
-    int grid = (int)std::min<long long>(n_tiles, (long long)fp.sm_count * ctas_per_sm);
-    if (grid <= 0) return 0;
-    k_barcode_fast<<<grid, kBarcodeWarps * 32, fp.barcode_smem, st>>>(fp.dev, t, wins, stride, n_windows, sel, dual, bmax0, bslots,
-                                                                  bc_score);
+    const long long n_tasks = dual ? 2 * n_windows : n_windows;
+    if (n_tasks <= 0) return 0;
+    const long long n_tiles = (n_tasks + kRowTile - 1) / kRowTile;
+    const size_t need_rows = (size_t)n_tiles * kRows * kRowTile * 4, need_meta = (size_t)n_tiles * kRowTile * sizeof(int4);
+    if (need_rows > fp.rowinfo_bytes) {
+        if (fp.rowinfo) cudaFree(fp.rowinfo);
+        fp.rowinfo = nullptr; fp.rowinfo_bytes = 0;
+        if (cudaMalloc(&fp.rowinfo, need_rows + need_rows / 8) != cudaSuccess) return 1;
+        fp.rowinfo_bytes = need_rows + need_rows / 8;
+    }
+    if (need_meta > fp.taskmeta_bytes) {
+        if (fp.taskmeta) cudaFree(fp.taskmeta);
+        fp.taskmeta = nullptr; fp.taskmeta_bytes = 0;
+        if (cudaMalloc(&fp.taskmeta, need_meta + need_meta / 8) != cudaSuccess) return 1;
+        fp.taskmeta_bytes = need_meta + need_meta / 8;
+    }
+    uint32_t *rowinfo = (uint32_t *)fp.rowinfo;
+    int4 *taskmeta = (int4 *)fp.taskmeta;
+    k_context<<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(fp.dev, t, codes, stride, n_windows, sel, dual, rowinfo, taskmeta);
     ++*launches;
+    {
+        int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (220 * 1024) / std::max<size_t>(1, fp.barcode_smem)));
+        int grid = (int)std::min<long long>(n_tiles, (long long)fp.sm_count * ctas_per_sm);
+        k_barcode_fast<<<grid, kBarcodeWarps * 32, fp.barcode_smem, st>>>(fp.dev, n_windows, dual, bmax0, bslots, rowinfo, taskmeta, bc_score);
+        ++*launches;
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
