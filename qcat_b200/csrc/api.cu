@@ -69,7 +69,11 @@ struct qcb_plan {
     FastPlan fast;                   // packed-kernel tables (kernels_fast.cuh)
     // workspace, sized per chunk of reads
     DeviceBuffer wins, codes, ad_score, ad_end, sel, bc_score, subset_dev, in_stage, out_stage, misc;
-    cudaStream_t stream = nullptr;   // used by the host-buffer entry points
+    cudaStream_t stream = nullptr;   // kernels of the host-buffer entry points
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;      // H2D / D2H of the host-buffer entry points
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    DeviceBuffer in_stage2[2], out_stage2[2];
+    long long host_chunk_reads = 1 << 16;
     long long launches = 0;
     bool profiling = false;
     struct StageEvent { int stage; cudaEvent_t a, b; long long launches; };
@@ -311,6 +315,9 @@ int detect_device_impl(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail
 }
 
 // Host-buffer path: stage -> device pipeline -> copy back, chunk by chunk.
+// Host-buffer path: H2D -> device pipeline -> D2H, chunk by chunk, software pipelined over three streams with
+// double-buffered staging so the copies of chunk k+1 / k-1 overlap the kernels of chunk k (pinned host memory makes
+// the copies truly asynchronous; pageable memory still works, just without the overlap).
 int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int32_t stride, const int32_t *wlen,
                      const int64_t *read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset,
                      qcb_result *out, int32_t *vote)
@@ -321,29 +328,50 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
     const bool window_mode = tail3 == nullptr;
     if (!win5 || !wlen || (!vote && !out) || (!vote && !window_mode && !read_len)) return fail("NULL input/output buffer");
     QCB_CUDA(cudaSetDevice(p->device));
-    cudaStream_t st = p->stream;
-    long long chunk = p->chunk_reads;
-    if ((long long)stride * chunk > (1LL << 28)) chunk = std::max<long long>(1, (1LL << 28) / stride);
-    for (long long off = 0; off < n_reads; off += chunk) {
+    cudaStream_t st = p->stream, s_in = p->copy_in, s_out = p->copy_out;
+    long long chunk = std::min<long long>(p->chunk_reads, p->host_chunk_reads);
+    if ((long long)stride * chunk > (1LL << 27)) chunk = std::max<long long>(1, (1LL << 27) / stride);
+    const size_t out_item = vote ? 4 : sizeof(qcb_result);
+    int rc = 0;
+    long long k = 0;
+    for (long long off = 0; off < n_reads && !rc; off += chunk, ++k) {
+        const int b = (int)(k & 1);
         long long n = std::min<long long>(chunk, n_reads - off);
         size_t b_win = (size_t)n * stride, b_len = (size_t)n * 4, b_rl = (size_t)n * 8;
         size_t o_tail = (b_win + 255) / 256 * 256, o_len = o_tail + (b_win + 255) / 256 * 256;
         size_t o_rl = o_len + (b_len + 255) / 256 * 256, total = o_rl + b_rl;
-        if (p->in_stage.reserve(total)) return 1;
-        if (p->out_stage.reserve((size_t)n * (vote ? 4 : sizeof(qcb_result)))) return 1;
-        uint8_t *d = (uint8_t *)p->in_stage.ptr;
-        QCB_CUDA(cudaMemcpyAsync(d, win5 + off * stride, b_win, cudaMemcpyHostToDevice, st));
-        if (!window_mode) QCB_CUDA(cudaMemcpyAsync(d + o_tail, tail3 + off * stride, b_win, cudaMemcpyHostToDevice, st));
-        QCB_CUDA(cudaMemcpyAsync(d + o_len, wlen + off, b_len, cudaMemcpyHostToDevice, st));
-        if (!vote && !window_mode) QCB_CUDA(cudaMemcpyAsync(d + o_rl, read_len + off, b_rl, cudaMemcpyHostToDevice, st));
-        if (detect_device_impl(p, d, window_mode ? nullptr : d + o_tail, stride, (const int32_t *)(d + o_len), (const int64_t *)(d + o_rl), n,
-                               subset, n_subset, vote ? nullptr : (qcb_result *)p->out_stage.ptr,
-                               vote ? (int32_t *)p->out_stage.ptr : nullptr, st))
-            return 1;
-        if (vote) QCB_CUDA(cudaMemcpyAsync(vote + off, p->out_stage.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        else QCB_CUDA(cudaMemcpyAsync(out + off, p->out_stage.ptr, (size_t)n * sizeof(qcb_result), cudaMemcpyDeviceToHost, st));
-        QCB_CUDA(cudaStreamSynchronize(st));
+        // staging buffer b was last used by chunk k-2: its kernels and its D2H must be done before it is reused
+        if (k >= 2) {
+            QCB_CUDA(cudaStreamWaitEvent(s_in, p->ev_compute[b], 0));
+            QCB_CUDA(cudaStreamWaitEvent(st, p->ev_d2h[b], 0));
+        }
+        if (p->in_stage2[b].bytes < total || p->out_stage2[b].bytes < (size_t)n * out_item) {
+            QCB_CUDA(cudaDeviceSynchronize());             // growing a staging buffer frees memory still in flight
+            if (p->in_stage2[b].reserve(total)) return 1;
+            if (p->out_stage2[b].reserve((size_t)n * out_item)) return 1;
+        }
+        uint8_t *d = (uint8_t *)p->in_stage2[b].ptr;
+        void *d_res = p->out_stage2[b].ptr;
+        QCB_CUDA(cudaMemcpyAsync(d, win5 + off * stride, b_win, cudaMemcpyHostToDevice, s_in));
+        if (!window_mode) QCB_CUDA(cudaMemcpyAsync(d + o_tail, tail3 + off * stride, b_win, cudaMemcpyHostToDevice, s_in));
+        QCB_CUDA(cudaMemcpyAsync(d + o_len, wlen + off, b_len, cudaMemcpyHostToDevice, s_in));
+        if (!vote && !window_mode) QCB_CUDA(cudaMemcpyAsync(d + o_rl, read_len + off, b_rl, cudaMemcpyHostToDevice, s_in));
+        QCB_CUDA(cudaEventRecord(p->ev_h2d[b], s_in));
+        QCB_CUDA(cudaStreamWaitEvent(st, p->ev_h2d[b], 0));
+        rc = detect_device_impl(p, d, window_mode ? nullptr : d + o_tail, stride, (const int32_t *)(d + o_len),
+                                (const int64_t *)(d + o_rl), n, subset, n_subset, vote ? nullptr : (qcb_result *)d_res,
+                                vote ? (int32_t *)d_res : nullptr, st);
+        if (rc) break;
+        QCB_CUDA(cudaEventRecord(p->ev_compute[b], st));
+        QCB_CUDA(cudaStreamWaitEvent(s_out, p->ev_compute[b], 0));
+        if (vote) QCB_CUDA(cudaMemcpyAsync(vote + off, d_res, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
+        else QCB_CUDA(cudaMemcpyAsync(out + off, d_res, (size_t)n * sizeof(qcb_result), cudaMemcpyDeviceToHost, s_out));
+        QCB_CUDA(cudaEventRecord(p->ev_d2h[b], s_out));
     }
+    cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(s_out);
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail("host path failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     return 0;
 }
 
@@ -375,7 +403,13 @@ qcb_plan *qcb_plan_create(const qcb_tables *tables, int device)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { fail("cudaGetDeviceProperties failed"); delete p; return nullptr; }
     p->sm_count = prop.multiProcessorCount;
     if (upload_tables(p, tables)) { delete p; return nullptr; }
-    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { fail("stream creation failed"); delete p; return nullptr; }
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking) != cudaSuccess) { fail("stream creation failed"); delete p; return nullptr; }
+    for (int i = 0; i < 2; ++i)
+        if (cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_compute[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_d2h[i], cudaEventDisableTiming) != cudaSuccess) { fail("event creation failed"); delete p; return nullptr; }
     if (fast_plan_build(p->fast, tables, p->sm_count)) { fail("fast-plan construction failed: %s", p->fast.error.c_str()); delete p; return nullptr; }
     return p;
 }
@@ -388,7 +422,15 @@ void qcb_plan_destroy(qcb_plan *p)
     p->wins.release(); p->codes.release(); p->ad_score.release(); p->ad_end.release(); p->sel.release(); p->bc_score.release();
     p->subset_dev.release(); p->in_stage.release(); p->out_stage.release(); p->misc.release();
     if (p->slab) cudaFree(p->slab);
+    for (int i = 0; i < 2; ++i) {
+        p->in_stage2[i].release(); p->out_stage2[i].release();
+        if (p->ev_h2d[i]) cudaEventDestroy(p->ev_h2d[i]);
+        if (p->ev_compute[i]) cudaEventDestroy(p->ev_compute[i]);
+        if (p->ev_d2h[i]) cudaEventDestroy(p->ev_d2h[i]);
+    }
     if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->copy_in) cudaStreamDestroy(p->copy_in);
+    if (p->copy_out) cudaStreamDestroy(p->copy_out);
     delete p;
 }
 
@@ -401,7 +443,7 @@ int qcb_plan_info(qcb_plan *p, qcb_plan_info_t *out)
     out->max_group_size = std::max(p->bmax0, p->bmax1);
     out->n_templates = p->t.n_templates;
     out->workspace_bytes = (int64_t)(p->wins.bytes + p->ad_score.bytes + p->ad_end.bytes + p->sel.bytes + p->bc_score.bytes +
-                                     p->in_stage.bytes + p->out_stage.bytes + p->fast.workspace_bytes());
+                                     p->in_stage2[0].bytes + p->in_stage2[1].bytes + p->out_stage2[0].bytes + p->out_stage2[1].bytes + p->fast.workspace_bytes());
     out->kernel_launches = p->launches;
     return 0;
 }
