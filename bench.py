@@ -27,6 +27,13 @@ if ROOT not in sys.path:
 ALGORITHMIC_BYTES_PER_READ = 336     # 2 x 150 B windows + 4 B length in, one 32 B record out
 CONFIG_INDEX = 2                     # BASELINE.json configs[2]: 96 barcodes, 1 -> 8 GPUs
 KIT = "PBC096"                       # the reference's 96-barcode EPI2ME kit (NBD196 does not exist in qcat 1.1.0)
+# Other BASELINE configs, selectable with --workload (parity-test cases, not the headline bench line):
+WORKLOADS = {
+    "configs[1]": ("NBD103/NBD104", "epi2me", "12-barcode NBD104 kit"),
+    "configs[2]": ("PBC096", "epi2me", "96-barcode PBC096 kit"),
+    "configs[3]": (None, "dual", "dual barcoding, 24 x 96 pairs (DUAL kit)"),
+    "configs[4]": ("PBC096", "epi2me", "96-barcode PBC096 kit, --trim (trim offsets are part of every record)"),
+}
 
 
 def parse_args():
@@ -38,8 +45,9 @@ def parse_args():
     ap.add_argument("--reads-per-step", type=int, default=1000000, help="reads per GPU per step")
     ap.add_argument("--unique-reads", type=int, default=262144, help="distinct synthetic reads generated (tiled up)")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="reads timed on the CPU oracle (cpu_baseline)")
-    ap.add_argument("--kit", default=KIT)
-    ap.add_argument("--mode", default="epi2me", choices=["epi2me", "dual"])
+    ap.add_argument("--workload", default="configs[2]", choices=sorted(WORKLOADS))
+    ap.add_argument("--kit", default=None)
+    ap.add_argument("--mode", default=None, choices=["epi2me", "dual"])
     ap.add_argument("--force-generic", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -161,8 +169,8 @@ def run_reference(args):
 
 
 def workload_config(args, reads_per_step):
-    return {"workload": "BASELINE configs[2]: 96-barcode %s kit, %s mode, 150 nt windows, synthetic reads mean 8 kb "
-                        "(8%% sub / 6%% del / 5%% ins on adapters, 10%% unbarcoded)" % (args.kit, args.mode),
+    return {"workload": "BASELINE %s: %s, %s mode, 150 nt windows, synthetic reads mean 8 kb "
+                        "(8%% sub / 6%% del / 5%% ins on adapters, 10%% unbarcoded)" % (args.workload, WORKLOADS[args.workload][2], args.mode),
             "kit": args.kit, "mode": args.mode, "reads_per_gpu_per_step": reads_per_step,
             "window": 150, "sharding": "reads sharded across ranks, one all-gather of per-barcode counts at the end",
             "l2": "inputs larger than L2 (%.0f MB per step per GPU)" % (reads_per_step * 332 / 1e6)}
@@ -211,6 +219,8 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    if world > 1:                                          # warm the communicator outside the timed region
+        dist.all_gather([torch.zeros_like(d_counts) for _ in range(world)], d_counts)
     barrier()
     d_counts.zero_()
     launches0 = plan.info()["kernel_launches"]
@@ -339,6 +349,11 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    kit, mode, _ = WORKLOADS[args.workload]
+    if args.mode is None:
+        args.mode = mode
+    if args.kit is None and args.mode != "dual":
+        args.kit = kit
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
