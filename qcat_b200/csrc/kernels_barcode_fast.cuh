@@ -21,77 +21,116 @@ __device__ __forceinline__ void decode_task(long long t, long long n_windows, in
 // Shared-context columns.  F[i] = H[i][u] + (i+u) g for the forward DP of region rows vs the shared prefix;
 // G[i] = H'[n-i][d] + (n-i+d) g for the DP of the reversed region vs the reversed shared suffix, whose left border
 // is 0 except -g at its last row (node (0, m) is not a valid end).  See DESIGN.md section 4.
-__global__ void __launch_bounds__(128)
-k_context(FastDev f, DevTables t, const uint8_t *__restrict__ codes, int stride, long long n_windows,
-          const WindowSel *__restrict__ sel, int dual, uint32_t *__restrict__ rowinfo, int4 *__restrict__ taskmeta)
-{
-    __shared__ int32_t s_sp[kMaxMatrix * kMaxMatrix];
-    for (int i = threadIdx.x; i < f.n_codes * f.n_codes; i += blockDim.x) s_sp[i] = f.sprime[i] - 2 * f.gap;   // plain M
-    __syncthreads();
-    const long long n_tasks = dual ? 2 * n_windows : n_windows;
-    const long long task = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (task >= n_tasks) return;
-    long long w; int k;
-    decode_task(task, n_windows, dual, w, k);
-    const WindowSel s = sel[w];
-    const int lo = k ? s.lo1 : s.lo0, hi = k ? s.hi1 : s.hi0;
-    const int grp = t.group[s.layout * 2 + k];
-    int n = hi - lo;
-    if (grp < 0 || n < 0) n = 0;
-    const FastGroup G = f.groups[grp < 0 ? 0 : grp];
-    const int g = f.gap, nc = f.n_codes;
-    const uint8_t *src = codes + w * stride + lo;
-    uint32_t *out = rowinfo + rowinfo_base(task);
+//
+// Packed: lane = one task, low u16 half = the F problem, high half = the G problem, both right-aligned in NCOL
+// registers (dead columns in front keep the border value).  Step s feeds region row s to F and row n-s+1 to G; the
+// per-group tables ctx_tab[grp][F|G][code][NCOL] hold the shifted scores (G's already moved to the high half), so a
+// cell is one three-input add and one VIMNMX3.U16x2.
+constexpr int kCtxWarps = 4;
 
-    int H[kMaxCtx + 1];
-    int cc[kMaxCtx];
-    // ---- forward: shared prefix ----
-    const int u = G.u, d = G.d;
+template <int NCOL>
+__global__ void __launch_bounds__(kCtxWarps * 32)
+k_context(FastDev f, DevTables t, const uint32_t *__restrict__ ctx_tab, const uint8_t *__restrict__ codes, int stride,
+          long long n_windows, const WindowSel *__restrict__ sel, int dual, uint32_t *__restrict__ rowinfo,
+          int4 *__restrict__ taskmeta)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nc = f.n_codes, g = f.gap;
+    const int tab_words = f.n_groups * 2 * nc * NCOL;
+    uint32_t *s_tab = (uint32_t *)smem;
+    uint8_t *s_code = smem + (size_t)tab_words * 4 + (size_t)warp * (kRows * kRowTile);
+    for (int i = threadIdx.x; i < tab_words; i += blockDim.x) s_tab[i] = ctx_tab[i];
+    __syncthreads();
+
+    const long long n_tasks = dual ? 2 * n_windows : n_windows;
+    const long long n_tiles = (n_tasks + kRowTile - 1) / kRowTile;
+    for (long long tile = (long long)blockIdx.x * kCtxWarps + warp; tile < n_tiles; tile += (long long)gridDim.x * kCtxWarps) {
+        const long long task = tile * kRowTile + lane;
+        const bool valid = task < n_tasks;
+        long long w; int k;
+        decode_task(valid ? task : 0, n_windows, dual, w, k);
+        const WindowSel s = sel[w];
+        const int lo = k ? s.lo1 : s.lo0, hi = k ? s.hi1 : s.hi0;
+        const int grp = t.group[s.layout * 2 + k];
+        int n = hi - lo;
+        if (!valid || grp < 0 || n < 0) n = 0;
+        const FastGroup G = f.groups[grp < 0 ? 0 : grp];
+        const int u = G.u, d = G.d;
+        __syncwarp();
+        {   // the lane's whole window: barcode-matrix code = high nibble of the packed code byte
+            const uint4 *src = (const uint4 *)(codes + w * stride);
+            const int last = n > 0 ? lo + n : 0;
+            for (int ch = 0; ch * 16 < last; ++ch) {
+                const uint4 v = src[ch];
+                const uint32_t words[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j <= kMaxCtx; ++j) H[j] = 0;
-#pragma unroll
-    for (int j = 0; j < kMaxCtx; ++j) cc[j] = j < u ? f.ctx_codes[G.up_off + j] : 0;
-    out[0] = (uint32_t)(u * g) << 4;
-    for (int i = 1; i <= n; ++i) {
-        const int code = src[i - 1] >> 4;
-        const int32_t *sp = s_sp + code * nc;
-        int diag = 0, left = 0;
-#pragma unroll
-        for (int j = 1; j <= kMaxCtx; ++j) {
-            if (j <= u) {
-                const int up = H[j];
-                const int h = max(max(diag + sp[cc[j - 1]], up - g), left - g);
-                diag = up; H[j] = h; left = h;
+                for (int b = 0; b < 16; ++b)
+                    s_code[(ch * 16 + b + 1) * kRowTile + lane] = (uint8_t)((words[b >> 2] >> ((b & 3) * 8 + 4)) & 15u);
             }
         }
-        out[(long long)i * kRowTile] = (uint32_t)code | ((uint32_t)(left + (i + u) * g) << 4);
-    }
-    int rup = INT32_MIN / 2;
+        __syncwarp();
+        const int nmax = __reduce_max_sync(0xffffffffu, n);
+        const uint32_t *tabF = s_tab + (size_t)(grp < 0 ? 0 : grp) * 2 * nc * NCOL;
+        const uint32_t *tabG = tabF + nc * NCOL;
+        uint32_t Wc[NCOL];
 #pragma unroll
-    for (int j = 1; j <= kMaxCtx; ++j)
-        if (j <= u) rup = max(rup, H[j]);
-    // ---- backward: shared suffix (reversed region vs reversed suffix) ----
+        for (int c = 0; c < NCOL; ++c) {
+            const int jf = c - (NCOL - u) + 1, jg = c - (NCOL - d) + 1;
+            Wc[c] = (uint32_t)(max(jf, 0) * g) | ((uint32_t)(max(jg, 0) * g) << 16);
+        }
+        // Row r of the packed output receives F at step r and G at step n - r.  Whichever comes first is a plain store,
+        // the later one ORs into it (same thread, so program order makes the read see the earlier store).
+        uint32_t *out = rowinfo + tile * (long long)(kRows * kRowTile) + lane;
+        if (n > 0) {
+            out[0] = (uint32_t)(u * g) << 4;                                  // F[0]
+            out[(long long)n * kRowTile] = (uint32_t)(d * g) << 18;            // G[n]: row 0 of the reversed problem
+        }
+        const uint32_t gdup = dup16((uint32_t)g);
+        uint32_t border = 0;
+        int rup = INT32_MIN / 2;
+        for (int st = 1; st <= nmax; ++st) {
+            const int cf = st <= n ? s_code[(lo + st) * kRowTile + lane] : 0;
+            const int cg = st <= n ? s_code[(lo + n - st + 1) * kRowTile + lane] : 0;
+            const uint4 *pf = (const uint4 *)(tabF + cf * NCOL);
+            const uint4 *pg = (const uint4 *)(tabG + cg * NCOL);
+            uint32_t diag = border;
+            border += gdup;
+            uint32_t left = border - (st == n ? ((uint32_t)g << 16) : 0u);      // G's left border at its last row is -g
+            uint32_t tt[NCOL];
 #pragma unroll
-    for (int j = 0; j <= kMaxCtx; ++j) H[j] = 0;
+            for (int c = 0; c < NCOL; c += 4) {
+                const uint4 ef = pf[c >> 2], eg = pg[c >> 2];
+                tt[c] = (c == 0 ? diag : Wc[c - 1]) + ef.x + eg.x;
+                tt[c + 1] = Wc[c] + ef.y + eg.y;
+                tt[c + 2] = Wc[c + 1] + ef.z + eg.z;
+                tt[c + 3] = Wc[c + 2] + ef.w + eg.w;
+            }
 #pragma unroll
-    for (int j = 0; j < kMaxCtx; ++j) cc[j] = j < d ? f.ctx_codes[G.down_off + d - 1 - j] : 0;
-    out[(long long)n * kRowTile] |= (uint32_t)(d * g) << 18;
-    for (int i = 1; i <= n; ++i) {
-        const int code = src[n - i] >> 4;
-        const int32_t *sp = s_sp + code * nc;
-        int diag = 0;
-        int left = (i == n) ? -g : 0;
+            for (int c = 0; c < NCOL; ++c) {
+                left = __vimax3_u16x2(tt[c], Wc[c], left);
+                Wc[c] = left;
+            }
+            if (st <= n) {
+                const uint32_t fword = (uint32_t)cf | ((left & 0xffffu) << 4), gword = (left >> 16) << 18;
+                uint32_t *pf_out = out + (long long)st * kRowTile, *pg_out = out + (long long)(n - st) * kRowTile;
+                if (2 * st < n) { *pf_out = fword; *pg_out = gword; }
+                else if (2 * st == n) { *pf_out = fword | gword; }
+                else { *pf_out |= fword; *pg_out |= gword; }
+            }
+            if (__any_sync(0xffffffffu, st == n)) {
+                if (st == n) {
 #pragma unroll
-        for (int j = 1; j <= kMaxCtx; ++j) {
-            if (j <= d) {
-                const int up = H[j];
-                const int h = max(max(diag + sp[cc[j - 1]], up - g), left - g);
-                diag = up; H[j] = h; left = h;
+                    for (int c = 0; c < NCOL; ++c) {
+                        const int jf = c - (NCOL - u) + 1;
+                        if (jf >= 1) rup = max(rup, (int)(Wc[c] & 0xffffu) - (n + jf) * g);
+                    }
+                }
             }
         }
-        out[(long long)(n - i) * kRowTile] |= (uint32_t)(left + (i + d) * g) << 18;
+        __syncwarp();
+        if (valid) taskmeta[task] = make_int4(n, grp, rup, 0);
     }
-    taskmeta[task] = make_int4(n, grp, rup, 0);
 }
 
 // Result of one (window, barcode pair): score = max(R over prefix columns, R over core columns, join with G).
@@ -149,7 +188,7 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots,
         const int npairs_max = __reduce_max_sync(0xffffffffu, n > 0 ? npairs : 0);
         const int v = G.u + (kCore - G.pad);            // last core column (template coordinates)
         int32_t *dst = bc_score + w * bslots + (k ? bmax0 : 0);
-        for (int pr = warp; pr < npairs_max; pr += kBarcodeWarps) {
+        for (int pr = warp; pr < npairs_max; pr += (int)(blockDim.x >> 5)) {
             const int pcl = min(pr, npairs - 1);
             const uint8_t *prow = (const uint8_t *)s_prof + G.prof_off + pcl * (f.n_codes * kProfWords * 4);
             uint32_t Wc[kCore];
@@ -158,32 +197,36 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots,
             const uint32_t info0 = s_row[lane];
             uint32_t Fprev = dup16((info0 >> 4) & 0x3fffu);
             uint32_t acc = dup16((uint32_t)(v * g)) + dup16(info0 >> 18);          // join term of row 0
-            for (int i = 1; i <= nmax; ++i) {
-                const uint32_t info = s_row[i * kRowTile + lane];
-                const uint4 *prow_i = (const uint4 *)(prow + (info & 15u) * (kProfWords * 4));
-                uint32_t e[kCore];
+            int i = 1;
+            while (i <= nmax) {
+                // rows up to the next row at which some lane's region ends run without per-lane branching; a lane's
+                // scores are taken at its own last row, so whatever it computes afterwards is never used
+                const int ev = __reduce_min_sync(0xffffffffu, n >= i ? n : INT32_MAX);
+                for (; i <= ev; ++i) {
+                    const uint32_t info = s_row[i * kRowTile + lane];
+                    const uint4 *prow_i = (const uint4 *)(prow + (info & 15u) * (kProfWords * 4));
+                    uint32_t e[kCore];
 #pragma unroll
-                for (int c = 0; c < kCore; c += 4) {
-                    const uint4 q = prow_i[c >> 2];
-                    e[c] = q.x; e[c + 1] = q.y; e[c + 2] = q.z; e[c + 3] = q.w;
-                }
-                const uint32_t Fi = dup16((info >> 4) & 0x3fffu);
-                const uint32_t Gi = dup16(info >> 18);
-                // diagonal terms first (previous row's registers), then the in-place left-to-right max chain
-                e[0] += Fprev;
+                    for (int c = 0; c < kCore; c += 4) {
+                        const uint4 q = prow_i[c >> 2];
+                        e[c] = q.x; e[c + 1] = q.y; e[c + 2] = q.z; e[c + 3] = q.w;
+                    }
+                    const uint32_t Fi = dup16((info >> 4) & 0x3fffu);
+                    const uint32_t Gi = dup16(info >> 18);
+                    // diagonal terms first (previous row's registers), then the in-place left-to-right max chain
+                    e[0] += Fprev;
 #pragma unroll
-                for (int c = 1; c < kCore; ++c) e[c] += Wc[c - 1];
-                uint32_t left = Fi;
+                    for (int c = 1; c < kCore; ++c) e[c] += Wc[c - 1];
+                    uint32_t left = Fi;
 #pragma unroll
-                for (int c = 0; c < kCore; ++c) {
-                    left = __vimax3_u16x2(e[c], Wc[c], left);
-                    Wc[c] = left;
+                    for (int c = 0; c < kCore; ++c) {
+                        left = __vimax3_u16x2(e[c], Wc[c], left);
+                        Wc[c] = left;
+                    }
+                    Fprev = Fi;
+                    acc = __viaddmax_u16x2(left, Gi, acc);
                 }
-                Fprev = Fi;
-                if (i <= n) acc = __viaddmax_u16x2(left, Gi, acc);
-                if (__any_sync(0xffffffffu, i == n)) {
-                    if (i == n && pr < npairs) store_pair_scores(Wc, acc, G, n, g, rup, pr, dst);
-                }
+                if (n == ev && pr < npairs) store_pair_scores(Wc, acc, G, n, g, rup, pr, dst);
             }
         }
     }

@@ -70,6 +70,10 @@ struct FastPlan {
     size_t slab_bytes = 0;
     int sm_count = 0;
     size_t barcode_smem = 0;
+    int max_pairs = 1;               // barcode pairs of the largest template group
+    const uint32_t *ctx_tab = nullptr;   // device: k_context score tables
+    int ctx_ncol = 12;
+    size_t context_smem = 0;
     void *rowinfo = nullptr;         // [tiles][kRows][32] u32: code | F << 4 | G << 18
     void *taskmeta = nullptr;        // [tasks] int4 {region length, group, R over prefix columns, -}
     size_t rowinfo_bytes = 0, taskmeta_bytes = 0;
@@ -328,6 +332,7 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
         if (core < 1 || core > kCore) return 0;
         if (smax * tlen + (kFastMaxStride + tlen) * g + 64 >= 16384) return 0;      // F / G are packed into 14 bits
         G.ok = 1; G.u = u; G.d = d; G.pad = kCore - core; G.tlen = tlen; G.nb = nb;
+        fp.max_pairs = std::max(fp.max_pairs, (nb + 1) / 2);
         G.up_off = (int32_t)ctx.size();
         for (int j = 0; j < u; ++j) ctx.push_back(h->bmap[first[j]]);
         G.down_off = (int32_t)ctx.size();
@@ -371,13 +376,34 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     std::vector<int32_t> sprime(nc * nc);
     for (int i = 0; i < nc * nc; ++i) sprime[i] = h->bmat[i] + 2 * g;
 
-    // one device slab: profile | groups | ctx | sprime
+    // k_context tables: ctx_tab[group][F | G][code][ncol] shifted scores of the shared prefix (low half) and of the
+    // reversed shared suffix (high half), right-aligned in ncol columns, 0 in the dead columns
+    int max_ctx = 0;
+    for (const FastGroup &G : groups) max_ctx = std::max(max_ctx, std::max(G.u, G.d));
+    const int ncol = max_ctx <= 12 ? 12 : 16;
+    std::vector<uint32_t> ctx_tab((size_t)ng * 2 * nc * ncol, 0u);
+    for (int gi = 0; gi < ng; ++gi) {
+        const FastGroup &G = groups[gi];
+        for (int code = 0; code < nc; ++code)
+            for (int c = 0; c < ncol; ++c) {
+                const int jf = c - (ncol - G.u) + 1, jg = c - (ncol - G.d) + 1;
+                if (jf >= 1) ctx_tab[(((size_t)gi * 2 + 0) * nc + code) * ncol + c] = (uint32_t)sprime[code * nc + ctx[G.up_off + jf - 1]];
+                if (jg >= 1) ctx_tab[(((size_t)gi * 2 + 1) * nc + code) * ncol + c] = (uint32_t)sprime[code * nc + ctx[G.down_off + G.d - jg]] << 16;
+            }
+    }
+    fp.ctx_ncol = ncol;
+    fp.context_smem = ctx_tab.size() * 4 + (size_t)kCtxWarps * kRows * kRowTile;
+    if (fp.context_smem > 200 * 1024) return 0;
+
+    // one device slab: profile | groups | ctx | sprime | ctx_tab
     size_t o_prof = 0;
     size_t o_grp = (o_prof + profile_bytes + 255) / 256 * 256;
     size_t o_ctx = (o_grp + groups.size() * sizeof(FastGroup) + 255) / 256 * 256;
     size_t o_sp = (o_ctx + ctx.size() + 16 + 255) / 256 * 256;
-    size_t total = o_sp + sprime.size() * 4;
+    size_t o_tab = (o_sp + sprime.size() * 4 + 255) / 256 * 256;
+    size_t total = o_tab + ctx_tab.size() * 4;
     std::vector<uint8_t> slab(total, 0);
+    memcpy(slab.data() + o_tab, ctx_tab.data(), ctx_tab.size() * 4);
     memcpy(slab.data() + o_prof, profile.data(), profile_bytes);
     memcpy(slab.data() + o_grp, groups.data(), groups.size() * sizeof(FastGroup));
     if (!ctx.empty()) memcpy(slab.data() + o_ctx, ctx.data(), ctx.size());
@@ -391,12 +417,15 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     fp.dev.groups = (const FastGroup *)(dptr + o_grp);
     fp.dev.ctx_codes = dptr + o_ctx;
     fp.dev.sprime = (const int32_t *)(dptr + o_sp);
+    fp.ctx_tab = (const uint32_t *)(dptr + o_tab);
     fp.dev.n_codes = nc;
     fp.dev.gap = g;
     fp.dev.n_groups = ng;
     fp.barcode_smem = profile_bytes + (size_t)kRows * kRowTile * 4;
     if (fp.barcode_smem > 220 * 1024) return 0;
-    if (cudaFuncSetAttribute(k_barcode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.barcode_smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_barcode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.barcode_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_context<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.context_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_context<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.context_smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -504,12 +533,28 @@ inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, const uint8_t *c
     }
     uint32_t *rowinfo = (uint32_t *)fp.rowinfo;
     int4 *taskmeta = (int4 *)fp.taskmeta;
-    k_context<<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(fp.dev, t, codes, stride, n_windows, sel, dual, rowinfo, taskmeta);
-    ++*launches;
     {
-        int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (220 * 1024) / std::max<size_t>(1, fp.barcode_smem)));
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / fp.context_smem));
+        const int cgrid = (int)std::min<long long>((n_tiles + kCtxWarps - 1) / kCtxWarps, (long long)fp.sm_count * per_sm);
+        if (fp.ctx_ncol == 12)
+            k_context<12><<<cgrid, kCtxWarps * 32, fp.context_smem, st>>>(fp.dev, t, fp.ctx_tab, codes, stride, n_windows, sel, dual, rowinfo, taskmeta);
+        else
+            k_context<16><<<cgrid, kCtxWarps * 32, fp.context_smem, st>>>(fp.dev, t, fp.ctx_tab, codes, stride, n_windows, sel, dual, rowinfo, taskmeta);
+        ++*launches;
+    }
+    {
+        // warps per CTA: every warp takes one barcode pair per round, so pick the count (<= 8) that wastes the fewest
+        // warp-rounds for this plan's largest set (6 pairs -> 6 warps, 48 pairs -> 8 warps), preferring more warps
+        int warps = kBarcodeWarps, best_waste = 1 << 30;
+        for (int wc = kBarcodeWarps; wc >= 4; --wc) {
+            int waste = (fp.max_pairs + wc - 1) / wc * wc - fp.max_pairs;
+            if (waste < best_waste) { best_waste = waste; warps = wc; }
+        }
+        const size_t regs_per_cta = (size_t)warps * 32 * 80;
+        int ctas_per_sm = (int)std::min<size_t>((220 * 1024) / std::max<size_t>(1, fp.barcode_smem), 65536 / regs_per_cta);
+        ctas_per_sm = std::max(1, std::min(ctas_per_sm, 8));
         int grid = (int)std::min<long long>(n_tiles, (long long)fp.sm_count * ctas_per_sm);
-        k_barcode_fast<<<grid, kBarcodeWarps * 32, fp.barcode_smem, st>>>(fp.dev, n_windows, dual, bmax0, bslots, rowinfo, taskmeta, bc_score);
+        k_barcode_fast<<<grid, warps * 32, fp.barcode_smem, st>>>(fp.dev, n_windows, dual, bmax0, bslots, rowinfo, taskmeta, bc_score);
         ++*launches;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
