@@ -106,9 +106,10 @@ int       qcb_plan_set_force_generic(qcb_plan *plan, int force);
 
 /* Per-stage device timing (CUDA events around each pipeline stage on the launching stream).  Off by default.
  * Stages: 0 orient (window extraction + revcomp), 1 adapter DP, 2 template selection / region geometry,
- * 3 barcode DP, 4 two-end decision (or kit vote).  qcb_plan_stage_times synchronises the recorded events,
- * adds the elapsed milliseconds of every launch since the last reset into ms[5] / launches[5]. */
-#define QCB_N_STAGES 5
+ * 3 barcode DP (core columns), 4 two-end decision (or kit vote), 5 shared-context columns of the barcode templates
+ * (packed path only).  qcb_plan_stage_times synchronises the recorded events and adds the elapsed milliseconds of
+ * every launch since the last reset into ms[QCB_N_STAGES] / launches[QCB_N_STAGES]. */
+#define QCB_N_STAGES 6
 int       qcb_plan_set_profiling(qcb_plan *plan, int enable);
 int       qcb_plan_stage_times(qcb_plan *plan, double *ms, int64_t *launches, int reset);
 

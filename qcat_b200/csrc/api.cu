@@ -78,8 +78,8 @@ struct qcb_plan {
     bool profiling = false;
     struct StageEvent { int stage; cudaEvent_t a, b; long long launches; };
     std::vector<StageEvent> stage_events;
-    double stage_ms[QCB_N_STAGES] = {0, 0, 0, 0, 0};
-    long long stage_launches[QCB_N_STAGES] = {0, 0, 0, 0, 0};
+    double stage_ms[QCB_N_STAGES] = {0, 0, 0, 0, 0, 0};
+    long long stage_launches[QCB_N_STAGES] = {0, 0, 0, 0, 0, 0};
     long long chunk_reads = 1 << 18;
 };
 
@@ -256,10 +256,15 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
     k_select<<<grid_for(nw, 256), 256, 0, st>>>(t, d_wlen, wshift, nw, d_subset, n_subset, ad_score, ad_end, sel);
     p->launches++;
     }
+    if (fast_ok && p->fast.barcode_ok) {
+        StageTimer timer(p, 5, st);
+        if (fast_context_stage(p->fast, t, (const uint8_t *)p->codes.ptr, stride, nw, sel, st, &p->launches))
+            return fail("shared-context stage launch failed");
+    }
     {
     StageTimer timer(p, 3, st);
     if (fast_ok && p->fast.barcode_ok) {
-        int rc = fast_barcode_stage(p->fast, t, (const uint8_t *)p->codes.ptr, stride, nw, sel, p->bmax0, bslots, bc_score, st, &p->launches);
+        int rc = fast_barcode_stage(p->fast, t, nw, p->bmax0, bslots, bc_score, st, &p->launches);
         if (rc) return fail("fast barcode stage launch failed");
     } else {
         k_barcode_generic<<<grid_for(nw * bslots, 128), 128, 0, st>>>(t, wins, stride, nw, sel, p->bmax0, bslots, bc_score);

@@ -510,9 +510,9 @@ inline int fast_adapter_stage(FastPlan &fp, const DevTables &, const uint8_t *co
     return rc;
 }
 
-inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, const uint8_t *codes, int stride, long long n_windows,
-                              const WindowSel *sel, int bmax0, int bslots, int32_t *bc_score, cudaStream_t st,
-                              long long *launches)
+// Shared-context columns of every (window, set) task -> plan-owned rowinfo / taskmeta buffers.
+inline int fast_context_stage(FastPlan &fp, const DevTables &t, const uint8_t *codes, int stride, long long n_windows,
+                              const WindowSel *sel, cudaStream_t st, long long *launches)
 {
     const int dual = t.mode == QCB_MODE_DUAL ? 1 : 0;
     const long long n_tasks = dual ? 2 * n_windows : n_windows;
@@ -542,6 +542,19 @@ inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, const uint8_t *c
             k_context<16><<<cgrid, kCtxWarps * 32, fp.context_smem, st>>>(fp.dev, t, fp.ctx_tab, codes, stride, n_windows, sel, dual, rowinfo, taskmeta);
         ++*launches;
     }
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// Core columns of every barcode against every task (needs fast_context_stage on the same stream first).
+inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, long long n_windows, int bmax0, int bslots, int32_t *bc_score,
+                              cudaStream_t st, long long *launches)
+{
+    const int dual = t.mode == QCB_MODE_DUAL ? 1 : 0;
+    const long long n_tasks = dual ? 2 * n_windows : n_windows;
+    if (n_tasks <= 0) return 0;
+    const long long n_tiles = (n_tasks + kRowTile - 1) / kRowTile;
+    const uint32_t *rowinfo = (const uint32_t *)fp.rowinfo;
+    const int4 *taskmeta = (const int4 *)fp.taskmeta;
     {
         // warps per CTA: every warp takes one barcode pair per round, so pick the count (<= 8) that wastes the fewest
         // warp-rounds for this plan's largest set (6 pairs -> 6 warps, 48 pairs -> 8 warps), preferring more warps

@@ -90,7 +90,7 @@ class DevicePlan(object):
     def set_force_generic(self, force):
         _ffi.check(self._lib.qcb_plan_set_force_generic(self._handle, 1 if force else 0))
 
-    STAGES = ("orient", "adapter", "select", "barcode", "decide")
+    STAGES = ("orient", "adapter", "select", "barcode", "decide", "context")
 
     def set_profiling(self, enable):
         _ffi.check(self._lib.qcb_plan_set_profiling(self._handle, 1 if enable else 0))
