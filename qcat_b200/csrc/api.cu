@@ -206,7 +206,10 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
     const long long nw = window_mode ? n : 2 * n;
     const DevTables &t = p->t;
     const int bslots = p->bmax0 + (t.mode == QCB_MODE_DUAL ? p->bmax1 : 0);
-    if (!window_mode && p->wins.reserve((size_t)nw * stride)) return 1;
+    // the ASCII copy of the oriented windows is only read by the generic kernels
+    const bool packed_only = !p->force_generic && !window_mode && p->fast.adapter_ok && p->fast.barcode_ok &&
+                             stride <= kFastMaxStride && (stride % 16) == 0 && n_subset <= 64;
+    if (!window_mode && !packed_only && p->wins.reserve((size_t)nw * stride)) return 1;
     if (p->ad_score.reserve((size_t)nw * n_subset * 4)) return 1;
     if (p->ad_end.reserve((size_t)nw * n_subset * 4)) return 1;
     const uint8_t *wins = d_win5;
@@ -218,7 +221,7 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
         if (fast_ok) {
             if (p->codes.reserve((size_t)nw * stride)) return 1;
             k_orient_codes<<<grid_for(nw * (stride / 4), 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, t.amap, t.bmap,
-                                                                          (uint8_t *)p->wins.ptr, (uint8_t *)p->codes.ptr);
+                                                                          packed_only ? nullptr : (uint8_t *)p->wins.ptr, (uint8_t *)p->codes.ptr);
         } else {
             k_orient<<<grid_for(nw * stride, 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, (uint8_t *)p->wins.ptr);
         }
@@ -235,6 +238,7 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
         if (adapter_rc == 1) return fail("fast adapter stage launch failed");
     }
     if (adapter_rc == 2) {
+        if (packed_only) return fail("internal: packed adapter stage unavailable after the ASCII windows were skipped");
         k_adapter_generic<<<grid_for(nw * n_subset, 128), 128, 0, st>>>(t, wins, stride, d_wlen, wshift, nw, d_subset, n_subset,
                                                                        ad_score, ad_end);
         p->launches++;
@@ -332,6 +336,11 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
     if (n_reads == 0) return 0;
     const bool window_mode = tail3 == nullptr;
     if (!win5 || !wlen || (!vote && !out) || (!vote && !window_mode && !read_len)) return fail("NULL input/output buffer");
+    for (int64_t i = 0; i < n_reads; ++i) {
+        const int32_t len = wlen[i];
+        if (len < 0 || len > stride || (!window_mode && len > p->t.W))
+            return fail("wlen[%lld] = %d outside [0, %d]", (long long)i, len, window_mode ? stride : std::min<int>(stride, p->t.W));
+    }
     QCB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = p->stream, s_in = p->copy_in, s_out = p->copy_out;
     long long chunk = std::min<long long>(p->chunk_reads, p->host_chunk_reads);

@@ -228,7 +228,7 @@ __global__ void k_orient_codes(const uint8_t *__restrict__ win5, const uint8_t *
     long long w = id / quads;
     int i0 = (int)(id % quads) * 4;
     long long r = w >> 1;
-    int len = wlen[r];
+    int len = min(max(wlen[r], 0), stride);
     uint32_t a = 0, c = 0;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -238,7 +238,7 @@ __global__ void k_orient_codes(const uint8_t *__restrict__ win5, const uint8_t *
         a |= (uint32_t)v << (8 * b);
         c |= (uint32_t)(i < len ? s_pack[v] : 0) << (8 * b);
     }
-    ((uint32_t *)wins)[id] = a;
+    if (wins) ((uint32_t *)wins)[id] = a;
     ((uint32_t *)codes)[id] = c;
 }
 

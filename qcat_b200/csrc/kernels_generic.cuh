@@ -89,7 +89,7 @@ __global__ void k_orient(const uint8_t *__restrict__ win5, const uint8_t *__rest
     long long w = id / stride;
     int i = (int)(id % stride);
     long long r = w >> 1;
-    int len = wlen[r];
+    int len = min(max(wlen[r], 0), stride);
     uint8_t v = 0;
     if (i < len) v = (w & 1) ? comp[tail3[r * stride + (len - 1 - i)]] : win5[r * stride + i];
     wins[id] = v;
