@@ -152,6 +152,36 @@ int qcb_kit_vote_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t *d_
 int qcb_histogram_device(qcb_plan *plan, const qcb_result *d_results, int64_t n_reads,
                          const int32_t *layout_bin_base, int64_t *d_counts, int32_t n_bins, void *stream);
 
+/* ---- host-side ingest / egress next to the path (no GPU involved) -------------------------------------------------
+ * What qcat/cli.py does in Python around detect_barcode_batch: record iteration (cli.py:235-306, Bio's
+ * FastqGeneralIterator / SimpleFastaParser), window extraction (scanner_base.py:223-244) and the per-barcode,
+ * optionally trimmed record output (cli.py:309-358, :521-552). */
+typedef struct {
+    int64_t title_off, title_len;   /* header line without '@' / '>' and without trailing whitespace */
+    int64_t seq_off, seq_span;      /* byte range of the sequence lines (may contain line breaks) */
+    int64_t seq_len;                /* bases */
+    int64_t qual_off, qual_span;    /* FASTQ quality lines; qual_off = -1 for FASTA */
+} qcb_fastx_record;
+
+const char *qcb_io_last_error(void);
+
+/* Index the complete records of an in-memory FASTQ / FASTA chunk.  *consumed = bytes covered by the records returned;
+ * call again from there with more data.  final_chunk != 0: the buffer ends the file (a last record without a trailing
+ * line break is complete).  Errors mirror the reference's ValueErrors (bad '@', missing '+', length mismatch). */
+int qcb_fastx_index(const char *buf, int64_t len, int32_t final_chunk, qcb_fastx_record *recs, int64_t max_records,
+                    int64_t *n_records, int64_t *consumed, int32_t *is_fastq);
+
+/* win5[i] = read[:W], tail3[i] = read[-W:], wlen, read_len for indexed records (the buffers qcb_detect takes). */
+int qcb_pack_windows(const char *buf, const qcb_fastx_record *recs, int64_t n, int32_t W, int32_t stride,
+                     uint8_t *win5, uint8_t *tail3, int32_t *wlen, int64_t *read_len, int32_t threads);
+
+/* Format records into per-bin byte strings ("@name comment\nSEQ\n+\nQUAL\n" / ">name comment\nSEQ\n"), trimmed to
+ * [trim5p:trim3p] when trim != 0 and dropped when shorter than min_read_length (cli.py:521-552 with -b).  Call once
+ * with out == NULL to obtain bin_bytes / bin_offset, then with a buffer of sum(bin_bytes).  kept[i] = record written. */
+int qcb_format_records(const char *buf, const qcb_fastx_record *recs, const qcb_result *results, const int32_t *bin, int64_t n,
+                       int32_t n_bins, int32_t fastq, int32_t trim, int64_t min_read_length,
+                       int64_t *bin_bytes, uint8_t *out, int64_t out_capacity, int64_t *bin_offset, uint8_t *kept, int32_t threads);
+
 /* Issue-rate micro-benchmark of the DP inner instruction pair on this device (compute-roofline
  * denominator): packed 16-bit DP cell updates per second the SMs can issue. */
 int qcb_microbench_cell_rate(int device, double *cells_per_second, double *sm_mhz_effective);

@@ -43,6 +43,10 @@ RESULT_DTYPE = np.dtype([("layout", "<i4"), ("barcode", "<i4"), ("barcode_score"
 assert RESULT_DTYPE.itemsize == ctypes.sizeof(QcbResult) == 32
 
 
+RECORD_DTYPE = np.dtype([("title_off", "<i8"), ("title_len", "<i8"), ("seq_off", "<i8"), ("seq_span", "<i8"),
+                         ("seq_len", "<i8"), ("qual_off", "<i8"), ("qual_span", "<i8")])      # qcb_fastx_record
+
+
 class QcbPlanInfo(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int32), ("sm_count", ctypes.c_int32), ("fast_adapter", ctypes.c_int32),
                 ("fast_barcode", ctypes.c_int32), ("max_group_size", ctypes.c_int32), ("n_templates", ctypes.c_int32),
@@ -97,7 +101,8 @@ def tables_struct(tables):
 # Every symbol include/qcat_b200.h declares (tests check the library exports all of them).
 EXPORTS = ("qcb_device_count", "qcb_last_error", "qcb_version", "qcb_plan_create", "qcb_plan_destroy", "qcb_plan_info",
            "qcb_plan_set_force_generic", "qcb_plan_set_profiling", "qcb_plan_stage_times", "qcb_sg_batch", "qcb_scan", "qcb_detect", "qcb_detect_device", "qcb_kit_vote",
-           "qcb_kit_vote_device", "qcb_histogram_device", "qcb_microbench_cell_rate")
+           "qcb_kit_vote_device", "qcb_histogram_device", "qcb_microbench_cell_rate", "qcb_io_last_error", "qcb_fastx_index",
+           "qcb_pack_windows", "qcb_format_records")
 
 _lib = None
 
@@ -147,6 +152,15 @@ def load():
     lib.qcb_histogram_device.argtypes = [vp, vp, ctypes.c_int64, vp, vp, ctypes.c_int32, vp]
     lib.qcb_microbench_cell_rate.restype = ctypes.c_int
     lib.qcb_microbench_cell_rate.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    lib.qcb_io_last_error.restype = ctypes.c_char_p
+    lib.qcb_io_last_error.argtypes = []
+    lib.qcb_fastx_index.restype = ctypes.c_int
+    lib.qcb_fastx_index.argtypes = [vp, ctypes.c_int64, ctypes.c_int32, vp, ctypes.c_int64, vp, vp, vp]
+    lib.qcb_pack_windows.restype = ctypes.c_int
+    lib.qcb_pack_windows.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp, ctypes.c_int32]
+    lib.qcb_format_records.restype = ctypes.c_int
+    lib.qcb_format_records.argtypes = [vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.c_int64, vp, vp, ctypes.c_int64, vp, vp, ctypes.c_int32]
     _lib = lib
     return lib
 

@@ -103,3 +103,39 @@ def test_cli_runs_unchanged_on_top_of_the_dropin(tmp_path):
     assert outputs["cpu"][0] == outputs["gpu"][0]
     assert outputs["cpu"][1] == outputs["gpu"][1]
     assert len(outputs["gpu"][1]) > 10          # many per-barcode files were written
+
+
+@pytest.mark.parametrize("kit,trim", [("PBC096", True), (None, False)])
+def test_native_demux_file_matches_reference_cli(tmp_path, kit, trim):
+    """qcat_b200.fastx.demux_file (native ingest + GPU scoring + native record writer) produces the same TSV and the
+    same per-barcode FASTQ files as the unmodified reference CLI on its CPU path, batch mode included (auto kit)."""
+    refloader.load()
+    from qcat import scanner as ref_scanner
+    from qcat_b200 import dropin, fastx
+    dropin.uninstall()
+    layouts = ref_scanner.factory(kit=kit or "RBK004").layouts
+    reads = _reads(layouts, 9000 if kit is None else 600, seed=11)        # > 2 CLI batches of 4000 in auto mode
+    fastq = tmp_path / "reads.fastq"
+    with open(fastq, "w") as fh:
+        for i, r in enumerate(reads):
+            fh.write("@read%d ch=%d\tstart=%d\n%s\n+\n%s\n" % (i, i % 512, i * 7, r, "#" * len(r)))
+    argv = ["-f", str(fastq), "--tsv", "-b", str(tmp_path / "cpu"), "--min-read-length", "200"]
+    if kit:
+        argv += ["-k", kit]
+    if trim:
+        argv += ["--trim"]
+    tsv_cpu = _run_cli(argv)
+    files_cpu = {name: open(tmp_path / "cpu" / name).read() for name in sorted(os.listdir(tmp_path / "cpu"))}
+
+    dropin.install(device=0)
+    try:
+        sc = ref_scanner.factory(kit=kit)
+        tsv = io.StringIO()
+        summary = fastx.demux_file(str(fastq), sc, trim=trim, min_read_length=200, out_dir=str(tmp_path / "gpu"), tsv=tsv,
+                                   chunk_bytes=1 << 20)
+    finally:
+        dropin.uninstall()
+    files_gpu = {name: open(tmp_path / "gpu" / name).read() for name in sorted(os.listdir(tmp_path / "gpu"))}
+    assert tsv.getvalue() == tsv_cpu
+    assert files_gpu == files_cpu
+    assert summary["reads"] == len(reads) and sum(summary["barcodes"].values()) == len(reads) - summary["skipped"]
