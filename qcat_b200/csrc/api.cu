@@ -68,7 +68,7 @@ struct qcb_plan {
     int max_adapter = 0, max_template = 0;
     FastPlan fast;                   // packed-kernel tables (kernels_fast.cuh)
     // workspace, sized per chunk of reads
-    DeviceBuffer wins, codes, ad_score, ad_end, sel, bc_score, subset_dev, in_stage, out_stage, misc;
+    DeviceBuffer wins, codes, ad_score, ad_end, sel, bc_score, subset_dev, misc;
     cudaStream_t stream = nullptr;   // kernels of the host-buffer entry points
     cudaStream_t copy_in = nullptr, copy_out = nullptr;      // H2D / D2H of the host-buffer entry points
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -434,7 +434,7 @@ void qcb_plan_destroy(qcb_plan *p)
     cudaSetDevice(p->device);
     fast_plan_free(p->fast);
     p->wins.release(); p->codes.release(); p->ad_score.release(); p->ad_end.release(); p->sel.release(); p->bc_score.release();
-    p->subset_dev.release(); p->in_stage.release(); p->out_stage.release(); p->misc.release();
+    p->subset_dev.release(); p->misc.release();
     if (p->slab) cudaFree(p->slab);
     for (int i = 0; i < 2; ++i) {
         p->in_stage2[i].release(); p->out_stage2[i].release();

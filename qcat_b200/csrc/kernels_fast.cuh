@@ -32,21 +32,18 @@ constexpr int kMaxCtx = 16;               // longest shared prefix / suffix hand
 constexpr int kMaxFastGroups = 64;
 
 struct FastGroup {          // one template group (layout, set k)
-    int32_t ok;             // group usable by the packed kernel
     int32_t u, d;           // shared prefix / suffix length (columns)
     int32_t pad;            // dead columns in front of the core (kCore - core length)
     int32_t tlen;           // template length (all templates of the group)
     int32_t nb;             // barcodes in the group
     int32_t prof_off;       // byte offset of the group's core-set profile inside the profile image
-    int32_t up_off, down_off;  // offsets of the context codes in ctx_codes
+    int32_t up_off, down_off;  // offsets of the context codes in the host-side ctx list (table construction only)
 };
 
 struct FastDev {
     const uint32_t *profile;     // [set][pair][code][kProfWords]
     int32_t profile_bytes;
     const FastGroup *groups;     // [n_groups]
-    const uint8_t *ctx_codes;    // barcode-matrix codes of the shared prefix / suffix columns
-    const int32_t *sprime;       // [bmat_size * bmat_size] M + 2g
     int32_t n_codes;             // bmat_size
     int32_t gap;                 // g
     int32_t n_groups;
@@ -331,7 +328,7 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
         while (core > kCore && u < kMaxCtx && nb == 1) { ++u; --core; }
         if (core < 1 || core > kCore) return 0;
         if (smax * tlen + (kFastMaxStride + tlen) * g + 64 >= 16384) return 0;      // F / G are packed into 14 bits
-        G.ok = 1; G.u = u; G.d = d; G.pad = kCore - core; G.tlen = tlen; G.nb = nb;
+        G.u = u; G.d = d; G.pad = kCore - core; G.tlen = tlen; G.nb = nb;
         fp.max_pairs = std::max(fp.max_pairs, (nb + 1) / 2);
         G.up_off = (int32_t)ctx.size();
         for (int j = 0; j < u; ++j) ctx.push_back(h->bmap[first[j]]);
@@ -369,10 +366,6 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
         G.prof_off = set_off[found];
     }
     const size_t profile_bytes = profile.size() * 4;
-    if (profile_bytes + 4 * kRows * kTile * 2 > 60 * 1024) {
-        // keep three CTAs per SM: profile + per-tile columns must stay under ~72 KB
-        if (profile_bytes > 150 * 1024) return 0;
-    }
     std::vector<int32_t> sprime(nc * nc);
     for (int i = 0; i < nc * nc; ++i) sprime[i] = h->bmat[i] + 2 * g;
 
@@ -395,19 +388,15 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     fp.context_smem = ctx_tab.size() * 4 + (size_t)kCtxWarps * kRows * kRowTile;
     if (fp.context_smem > 200 * 1024) return 0;
 
-    // one device slab: profile | groups | ctx | sprime | ctx_tab
+    // one device slab: profile | groups | ctx_tab
     size_t o_prof = 0;
     size_t o_grp = (o_prof + profile_bytes + 255) / 256 * 256;
-    size_t o_ctx = (o_grp + groups.size() * sizeof(FastGroup) + 255) / 256 * 256;
-    size_t o_sp = (o_ctx + ctx.size() + 16 + 255) / 256 * 256;
-    size_t o_tab = (o_sp + sprime.size() * 4 + 255) / 256 * 256;
+    size_t o_tab = (o_grp + groups.size() * sizeof(FastGroup) + 255) / 256 * 256;
     size_t total = o_tab + ctx_tab.size() * 4;
     std::vector<uint8_t> slab(total, 0);
     memcpy(slab.data() + o_tab, ctx_tab.data(), ctx_tab.size() * 4);
     memcpy(slab.data() + o_prof, profile.data(), profile_bytes);
     memcpy(slab.data() + o_grp, groups.data(), groups.size() * sizeof(FastGroup));
-    if (!ctx.empty()) memcpy(slab.data() + o_ctx, ctx.data(), ctx.size());
-    memcpy(slab.data() + o_sp, sprime.data(), sprime.size() * 4);
     if (cudaMalloc(&fp.slab, total) != cudaSuccess) { fp.error = "cudaMalloc failed"; return 1; }
     fp.slab_bytes = total;
     if (cudaMemcpy(fp.slab, slab.data(), total, cudaMemcpyHostToDevice) != cudaSuccess) { fp.error = "cudaMemcpy failed"; return 1; }
@@ -415,8 +404,6 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     fp.dev.profile = (const uint32_t *)(dptr + o_prof);
     fp.dev.profile_bytes = (int32_t)profile_bytes;
     fp.dev.groups = (const FastGroup *)(dptr + o_grp);
-    fp.dev.ctx_codes = dptr + o_ctx;
-    fp.dev.sprime = (const int32_t *)(dptr + o_sp);
     fp.ctx_tab = (const uint32_t *)(dptr + o_tab);
     fp.dev.n_codes = nc;
     fp.dev.gap = g;

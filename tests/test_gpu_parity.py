@@ -121,6 +121,9 @@ def test_custom_config_uses_generic_kernels(engine):
     data = synth.generate(sc.layouts, 3000, seed=5, W=120, stride=128)
     tables = Tables(sc.layouts, cfg, "epi2me", sc.min_quality)
     plan = engine.DevicePlan(tables, device=0)
+    info = plan.info()
+    assert info["fast_adapter"] == 0, "affine gaps (open != extend) must select the generic adapter kernel"
+    assert info["fast_barcode"] == 1, "the barcode scheme is fixed at 1/1 (scanner_base.py:115-116): packed kernel"
     got = plan.detect(data["win5"], data["tail3"], data["wlen"], data["read_len"])
     want = helpers.oracle_detect(tables, data["win5"], data["tail3"], data["wlen"], data["read_len"])
     helpers.assert_records_equal(got, want, "custom config")
