@@ -182,6 +182,40 @@ int qcb_format_records(const char *buf, const qcb_fastx_record *recs, const qcb_
                        int32_t n_bins, int32_t fastq, int32_t trim, int64_t min_read_length,
                        int64_t *bin_bytes, uint8_t *out, int64_t out_capacity, int64_t *bin_offset, uint8_t *kept, int32_t threads);
 
+/* Same as qcb_fastx_index with the scan spread over `threads` threads: the buffer is cut at record starts found by a
+ * local test ('@' line, '+' two lines later, equal sequence / quality line lengths) that each neighbouring scan then
+ * confirms by arriving exactly there; anything else (wrapped FASTQ, malformed input) falls back to the serial scan, so
+ * results and errors are those of qcb_fastx_index. */
+int qcb_fastx_index_mt(const char *buf, int64_t len, int32_t final_chunk, qcb_fastx_record *recs, int64_t max_records,
+                       int64_t *n_records, int64_t *consumed, int32_t *is_fastq, int32_t threads);
+
+/* The CLI's default single output stream (cli.py:337-352): every kept record in input order with " barcode=<label>"
+ * appended to its comment.  label[i] indexes a caller-provided table of strings (labels + label_off[n_labels + 1]):
+ * str(barcode.id) or "none".  *out_bytes = size needed; nothing is written when out == NULL. */
+int qcb_format_stream(const char *buf, const qcb_fastx_record *recs, const qcb_result *results, const int32_t *label, int64_t n,
+                      const char *labels, const int64_t *label_off, int32_t n_labels, int32_t fastq, int32_t trim,
+                      int64_t min_read_length, uint8_t *out, int64_t out_capacity, int64_t *out_bytes, uint8_t *kept, int32_t threads);
+
+/* The --tsv table (cli.py:408-442) without its header line: name, length after trimming, barcode id, repr(score), kit,
+ * adapter_end, comment ("None" when the header has none); unclassified records (label[i] < 0) get none / -1 / none / -1. */
+int qcb_format_tsv(const char *buf, const qcb_fastx_record *recs, const qcb_result *results, const int32_t *label,
+                   const int32_t *kit_label, int64_t n, const char *labels, const int64_t *label_off, int32_t n_labels,
+                   int32_t trim, int64_t min_read_length, uint8_t *out, int64_t out_capacity, int64_t *out_bytes,
+                   uint8_t *kept, int32_t threads);
+
+/* Chunked reader replacing iter_fastx (cli.py:235-306) for files: qcb_reader_next() returns the next chunk of complete
+ * records (bytes read with `threads` concurrent preads, indexed with qcb_fastx_index_mt); every chunk but the last holds
+ * a multiple of `multiple_of` records so that CLI batches of 4000 stay aligned.  *chunk = NULL at the end of the file.
+ * A chunk stays valid until qcb_chunk_release(); chunks may be released from another thread than the reading one. */
+typedef struct qcb_reader qcb_reader;
+typedef struct qcb_chunk qcb_chunk;
+qcb_reader *qcb_reader_open(const char *path, int64_t chunk_bytes, int32_t threads);
+int qcb_reader_next(qcb_reader *reader, int64_t multiple_of, qcb_chunk **chunk);
+const char *qcb_chunk_data(const qcb_chunk *chunk, int64_t *len);
+const qcb_fastx_record *qcb_chunk_records(const qcb_chunk *chunk, int64_t *n_records, int32_t *is_fastq);
+void qcb_chunk_release(qcb_chunk *chunk);
+void qcb_reader_close(qcb_reader *reader);
+
 /* Issue-rate micro-benchmark of the DP inner instruction pair on this device (compute-roofline
  * denominator): packed 16-bit DP cell updates per second the SMs can issue. */
 int qcb_microbench_cell_rate(int device, double *cells_per_second, double *sm_mhz_effective);

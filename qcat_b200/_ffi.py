@@ -102,7 +102,8 @@ def tables_struct(tables):
 EXPORTS = ("qcb_device_count", "qcb_last_error", "qcb_version", "qcb_plan_create", "qcb_plan_destroy", "qcb_plan_info",
            "qcb_plan_set_force_generic", "qcb_plan_set_profiling", "qcb_plan_stage_times", "qcb_sg_batch", "qcb_scan", "qcb_detect", "qcb_detect_device", "qcb_kit_vote",
            "qcb_kit_vote_device", "qcb_histogram_device", "qcb_microbench_cell_rate", "qcb_io_last_error", "qcb_fastx_index",
-           "qcb_pack_windows", "qcb_format_records")
+           "qcb_pack_windows", "qcb_format_records", "qcb_fastx_index_mt", "qcb_format_stream", "qcb_format_tsv",
+           "qcb_reader_open", "qcb_reader_next", "qcb_chunk_data", "qcb_chunk_records", "qcb_chunk_release", "qcb_reader_close")
 
 _lib = None
 
@@ -161,6 +162,25 @@ def load():
     lib.qcb_format_records.restype = ctypes.c_int
     lib.qcb_format_records.argtypes = [vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                        ctypes.c_int64, vp, vp, ctypes.c_int64, vp, vp, ctypes.c_int32]
+    i32, i64 = ctypes.c_int32, ctypes.c_int64
+    lib.qcb_fastx_index_mt.restype = ctypes.c_int
+    lib.qcb_fastx_index_mt.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, i32]
+    lib.qcb_format_stream.restype = ctypes.c_int
+    lib.qcb_format_stream.argtypes = [vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, i64, vp, i64, vp, vp, i32]
+    lib.qcb_format_tsv.restype = ctypes.c_int
+    lib.qcb_format_tsv.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, i64, vp, i64, vp, vp, i32]
+    lib.qcb_reader_open.restype = vp
+    lib.qcb_reader_open.argtypes = [ctypes.c_char_p, i64, i32]
+    lib.qcb_reader_next.restype = ctypes.c_int
+    lib.qcb_reader_next.argtypes = [vp, i64, ctypes.POINTER(vp)]
+    lib.qcb_chunk_data.restype = vp
+    lib.qcb_chunk_data.argtypes = [vp, ctypes.POINTER(i64)]
+    lib.qcb_chunk_records.restype = vp
+    lib.qcb_chunk_records.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i32)]
+    lib.qcb_chunk_release.restype = None
+    lib.qcb_chunk_release.argtypes = [vp]
+    lib.qcb_reader_close.restype = None
+    lib.qcb_reader_close.argtypes = [vp]
     _lib = lib
     return lib
 

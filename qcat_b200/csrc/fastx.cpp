@@ -4,12 +4,20 @@
 // (cli.py:309-358, :521-552) -- on in-memory buffers, multi-threaded where records are independent.
 // No CUDA in this file; it is part of libqcat_b200.so so the binding stays one library.
 #include <algorithm>
+#include <charconv>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/qcat_b200.h"
 
@@ -82,24 +90,13 @@ inline int copy_tail(const char *begin, const char *end, uint8_t *dst, int want)
     return k;
 }
 
-}  // namespace
-
-extern "C" {
-
-const char *qcb_io_last_error(void) { return g_io_error.c_str(); }
-
-int qcb_fastx_index(const char *buf, int64_t len, int32_t final_chunk, qcb_fastx_record *recs, int64_t max_records,
-                    int64_t *n_records, int64_t *consumed, int32_t *is_fastq)
+// Serial record scan of [start, end); offsets are relative to `base`.  `final_chunk`: the range ends the input (a last
+// record without a line break is complete).  Stops after max_records.  *done = end of the last complete record.
+int index_range(const char *base, const char *start, const char *end, bool fastq, bool final_chunk,
+                qcb_fastx_record *recs, int64_t max_records, int64_t *n_records, const char **done_out)
 {
-    if (!buf || !recs || !n_records || !consumed || !is_fastq) return io_fail("NULL argument");
-    const char *p = buf, *end = buf + len;
-    *n_records = 0; *consumed = 0;
-    while (p < end && (*p == '\n' || *p == '\r')) ++p;
-    if (p >= end) { *consumed = len; return 0; }
-    if (*p != '@' && *p != '>')
-        return io_fail("Invalid input file. File must start with '@' or '>'. Current file starts with: %c", *p);
-    const bool fastq = *p == '@';
-    *is_fastq = fastq ? 1 : 0;
+    const char *buf = base;
+    const char *p = start;
     int64_t n = 0;
     const char *done = p;                 // everything before `done` belongs to complete records
     while (p < end && n < max_records) {
@@ -173,8 +170,168 @@ int qcb_fastx_index(const char *buf, int64_t len, int32_t final_chunk, qcb_fastx
         done = p;
     }
     *n_records = n;
+    *done_out = done;
+    return 0;
+}
+
+// First line start at or after `from` that begins a record, or NULL.  FASTA: any line starting with '>' (sequence lines
+// never do).  FASTQ: a line starting with '@' whose line + 2 starts with '+' and whose lines + 1 and + 3 have equal
+// lengths -- in the 4-line layout a quality line starting with '@' is followed two lines later by bases, never by '+'.
+// Wrapped FASTQ can defeat this test; index_parallel() therefore verifies every sync point against the scan that
+// reaches it from the left and falls back to the serial scan otherwise.
+const char *find_sync(const char *buf, const char *from, const char *end, bool fastq)
+{
+    const char *p = from;
+    if (p > buf) {                                                   // advance to a line start
+        const char *q = (const char *)memchr(p - 1, '\n', (size_t)(end - (p - 1)));
+        if (!q) return nullptr;
+        p = q + 1;
+    }
+    while (p < end) {
+        const char *e0 = line_end(p, end);
+        if (*p == (fastq ? '@' : '>')) {
+            if (!fastq) return p;
+            if (e0 < end) {
+                const char *l1 = e0 + 1, *e1 = line_end(l1, end);
+                if (e1 < end) {
+                    const char *l2 = e1 + 1, *e2 = line_end(l2, end);
+                    if (*l2 == '+' && e2 < end) {
+                        const char *l3 = e2 + 1, *e3 = line_end(l3, end);
+                        if (rstrip_len(l1, e1) == rstrip_len(l3, e3) && (e3 + 1 >= end || e3[1] == '@')) return p;
+                    }
+                }
+            }
+        }
+        if (e0 >= end) break;
+        p = e0 + 1;
+    }
+    return nullptr;
+}
+
+struct Segment {
+    const char *start = nullptr, *stop = nullptr;
+    std::vector<qcb_fastx_record> recs;
+    const char *done = nullptr;
+    int rc = 0;
+    std::string err;
+};
+
+// Parallel scan: cut [p, end) at verified record starts, scan the pieces concurrently, concatenate.  Returns -1 when
+// the pieces do not line up (the caller then scans serially), otherwise index_range's return code.
+int index_parallel(const char *buf, const char *p, const char *end, bool fastq, bool final_chunk, int threads,
+                   qcb_fastx_record *recs, int64_t max_records, int64_t *n_records, const char **done_out)
+{
+    const int64_t len = end - p;
+    std::vector<Segment> seg;
+    {
+        Segment s0; s0.start = p; seg.push_back(s0);
+        for (int t = 1; t < threads; ++t) {
+            const char *from = p + len * t / threads;
+            if (from <= seg.back().start) continue;
+            const char *s = find_sync(buf, from, end, fastq);
+            if (!s || s <= seg.back().start) continue;
+            Segment sn; sn.start = s; seg.push_back(sn);
+        }
+        for (size_t i = 0; i < seg.size(); ++i) seg[i].stop = i + 1 < seg.size() ? seg[i + 1].start : end;
+    }
+    if (seg.size() < 2) return -1;
+    std::vector<std::thread> pool;
+    for (size_t i = 0; i < seg.size(); ++i) {
+        pool.emplace_back([&, i]() {
+            Segment &s = seg[i];
+            const bool last = i + 1 == seg.size();
+            const int64_t span = s.stop - s.start;
+            int64_t cap = std::max<int64_t>(1024, span / 64);
+            for (;;) {                                               // grow-and-retry keeps the scan allocation-light
+                s.recs.resize((size_t)cap);
+                int64_t n = 0;
+                s.rc = index_range(buf, s.start, s.stop, fastq, last ? final_chunk : true, s.recs.data(), cap, &n, &s.done);
+                if (s.rc != 0) { s.err = g_io_error; s.recs.clear(); return; }
+                if (n < cap || s.done >= s.stop) { s.recs.resize((size_t)n); return; }
+                cap *= 4;
+            }
+        });
+    }
+    for (auto &th : pool) th.join();
+    int64_t total = 0;
+    for (size_t i = 0; i < seg.size(); ++i) {
+        const Segment &s = seg[i];
+        const bool last = i + 1 == seg.size();
+        if (s.rc != 0) {
+            // an inner piece that fails may just have been cut at a false sync point: let the serial scan decide
+            if (!last || i > 0) return -1;
+            g_io_error = s.err;
+            return s.rc;
+        }
+        if (!last && s.done != s.stop) return -1;                    // did not land on the next sync point
+        total += (int64_t)s.recs.size();
+    }
+    int64_t n = 0;
+    const char *done = p;
+    for (const Segment &s : seg) {
+        const int64_t take = std::min<int64_t>((int64_t)s.recs.size(), max_records - n);
+        if (take > 0) memcpy(recs + n, s.recs.data(), (size_t)take * sizeof(qcb_fastx_record));
+        n += take;
+        if (take < (int64_t)s.recs.size()) {                         // max_records reached inside this piece
+            done = buf + s.recs[(size_t)take].title_off - 1;
+            *n_records = n; *done_out = done;
+            return 0;
+        }
+        done = s.done;
+    }
+    (void)total;
+    *n_records = n;
+    *done_out = done;
+    return 0;
+}
+
+// Scan [p, end) whose first byte starts a record (or blank lines): parallel when worthwhile, serial otherwise.
+int index_from(const char *buf, const char *p, const char *end, bool fastq, bool final_chunk, int threads,
+               qcb_fastx_record *recs, int64_t max_records, int64_t *n_records, const char **done)
+{
+    int rc = -1;
+    *done = p;
+    if (threads > 1 && end - p >= (int64_t)1 << 20)
+        rc = index_parallel(buf, p, end, fastq, final_chunk, threads, recs, max_records, n_records, done);
+    if (rc < 0) rc = index_range(buf, p, end, fastq, final_chunk, recs, max_records, n_records, done);
+    return rc;
+}
+
+int index_buffer(const char *buf, int64_t len, int32_t final_chunk, qcb_fastx_record *recs, int64_t max_records,
+                 int64_t *n_records, int64_t *consumed, int32_t *is_fastq, int threads)
+{
+    if (!buf || !recs || !n_records || !consumed || !is_fastq) return io_fail("NULL argument");
+    const char *p = buf, *end = buf + len;
+    *n_records = 0; *consumed = 0;
+    while (p < end && (*p == '\n' || *p == '\r')) ++p;
+    if (p >= end) { *consumed = len; return 0; }
+    if (*p != '@' && *p != '>')
+        return io_fail("Invalid input file. File must start with '@' or '>'. Current file starts with: %c", *p);
+    const bool fastq = *p == '@';
+    *is_fastq = fastq ? 1 : 0;
+    const char *done = p;
+    const int rc = index_from(buf, p, end, fastq, final_chunk != 0, threads, recs, max_records, n_records, &done);
+    if (rc != 0) return rc;
     *consumed = done - buf;
     return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *qcb_io_last_error(void) { return g_io_error.c_str(); }
+
+int qcb_fastx_index(const char *buf, int64_t len, int32_t final_chunk, qcb_fastx_record *recs, int64_t max_records,
+                    int64_t *n_records, int64_t *consumed, int32_t *is_fastq)
+{
+    return index_buffer(buf, len, final_chunk, recs, max_records, n_records, consumed, is_fastq, 1);
+}
+
+int qcb_fastx_index_mt(const char *buf, int64_t len, int32_t final_chunk, qcb_fastx_record *recs, int64_t max_records,
+                       int64_t *n_records, int64_t *consumed, int32_t *is_fastq, int32_t threads)
+{
+    return index_buffer(buf, len, final_chunk, recs, max_records, n_records, consumed, is_fastq, threads);
 }
 
 int qcb_pack_windows(const char *buf, const qcb_fastx_record *recs, int64_t n, int32_t W, int32_t stride,
@@ -273,6 +430,400 @@ int qcb_format_records(const char *buf, const qcb_fastx_record *recs, const qcb_
         }
     });
     return 0;
+}
+
+// ---- one output stream and the TSV table -------------------------------------------------------------------------------
+
+namespace {
+
+struct Cut { int64_t a, b; };
+
+// Python slice semantics of seq[trim5p:trim3p] for 0 <= trims (cli.py:521-526)
+inline Cut trimmed_range(const qcb_fastx_record &r, const qcb_result &res, int trim)
+{
+    Cut c{0, r.seq_len};
+    if (trim) {
+        c.a = std::min<int64_t>(std::max<int64_t>(res.trim5p, 0), r.seq_len);
+        c.b = std::min<int64_t>(std::max<int64_t>(res.trim3p, 0), r.seq_len);
+        if (c.b < c.a) c.b = c.a;
+    }
+    return c;
+}
+
+// repr(float) of Python 3 for the magnitudes a score can take (1e-4 <= |x| < 1e16, or 0): shortest round-trip digits
+inline char *put_float_repr(char *o, double v)
+{
+    auto r = std::to_chars(o, o + 40, v, std::chars_format::fixed);
+    bool dot = false;
+    for (char *q = o; q < r.ptr; ++q) if (*q == '.') dot = true;
+    char *e = r.ptr;
+    if (!dot) { *e++ = '.'; *e++ = '0'; }
+    return e;
+}
+
+inline char *put_int(char *o, long long v)
+{
+    return std::to_chars(o, o + 24, v).ptr;
+}
+
+}  // namespace
+
+// The default output of the CLI (no -b): every kept record, input order, on one stream with "barcode=<id>" appended to
+// the comment (cli.py:337-352): "@name comment barcode=ID\nSEQ\n+\nQUAL\n" / ">name comment barcode=ID\nSEQ\n".
+// label[i] indexes the caller's label table (labels / label_off: concatenated strings); the label of a record is
+// str(barcode.id) or "none".  out_bytes = bytes needed; nothing is written when out == NULL or the capacity is short.
+int qcb_format_stream(const char *buf, const qcb_fastx_record *recs, const qcb_result *results, const int32_t *label, int64_t n,
+                      const char *labels, const int64_t *label_off, int32_t n_labels, int32_t fastq, int32_t trim,
+                      int64_t min_read_length, uint8_t *out, int64_t out_capacity, int64_t *out_bytes, uint8_t *kept, int32_t threads)
+{
+    if (!out_bytes) return io_fail("NULL argument");
+    *out_bytes = 0;
+    if (n == 0) return 0;
+    if (!buf || !recs || !results || !label || !labels || !label_off || !kept) return io_fail("NULL argument");
+    std::vector<int64_t> pos((size_t)n + 1);
+    for (int64_t i = 0; i < n; ++i) {
+        const qcb_fastx_record &r = recs[i];
+        if (label[i] < 0 || label[i] >= n_labels) return io_fail("label[%lld] out of range", (long long)i);
+        if (r.seq_span != r.seq_len || (fastq && r.qual_span != r.seq_len)) return io_fail("multi-line records are not supported by the native writer");
+    }
+    parallel_for(n, threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            const qcb_fastx_record &r = recs[i];
+            const Cut c = trimmed_range(r, results[i], trim);
+            const int64_t m = c.b - c.a;
+            kept[i] = m >= min_read_length ? 1 : 0;
+            const bool blank = memchr(buf + r.title_off, ' ', (size_t)r.title_len) || memchr(buf + r.title_off, '\t', (size_t)r.title_len);
+            const int64_t lab = label_off[label[i] + 1] - label_off[label[i]];
+            pos[(size_t)i + 1] = kept[i] ? 1 + r.title_len + (blank ? 0 : 1) + 9 + lab + 1 + m + 1 + (fastq ? 2 + m + 1 : 0) : 0;
+        }
+    });
+    pos[0] = 0;
+    for (int64_t i = 0; i < n; ++i) pos[(size_t)i + 1] += pos[(size_t)i];
+    *out_bytes = pos[(size_t)n];
+    if (!out) return 0;
+    if (pos[(size_t)n] > out_capacity) return io_fail("output buffer too small: need %lld bytes", (long long)pos[(size_t)n]);
+    parallel_for(n, threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            if (!kept[i]) continue;
+            const qcb_fastx_record &r = recs[i];
+            const Cut c = trimmed_range(r, results[i], trim);
+            uint8_t *o = out + pos[(size_t)i];
+            *o++ = fastq ? '@' : '>';
+            bool blank = false;
+            for (int64_t j = 0; j < r.title_len; ++j) {
+                char ch = buf[r.title_off + j];
+                if (ch == '\t') ch = ' ';
+                if (ch == ' ') blank = true;
+                *o++ = (uint8_t)ch;
+            }
+            if (!blank) *o++ = ' ';
+            memcpy(o, " barcode=", 9); o += 9;
+            const int64_t l0 = label_off[label[i]], l1 = label_off[label[i] + 1];
+            memcpy(o, labels + l0, (size_t)(l1 - l0)); o += l1 - l0;
+            *o++ = '\n';
+            memcpy(o, buf + r.seq_off + c.a, (size_t)(c.b - c.a)); o += c.b - c.a;
+            *o++ = '\n';
+            if (fastq) {
+                *o++ = '+'; *o++ = '\n';
+                memcpy(o, buf + r.qual_off + c.a, (size_t)(c.b - c.a)); o += c.b - c.a;
+                *o++ = '\n';
+            }
+        }
+    });
+    return 0;
+}
+
+// The --tsv table (cli.py:408-442), one line per kept record, input order, without the header line:
+//   name \t len(sequence after trimming) \t barcode.id \t repr(score) \t kit \t adapter_end \t comment
+// or  name \t len \t none \t -1 \t none \t -1 \t comment  for unclassified reads; comment = "None" when the header has
+// no blank.  label[i] / kit_label[i] index the caller's label table (ignored for unclassified records, label[i] < 0).
+int qcb_format_tsv(const char *buf, const qcb_fastx_record *recs, const qcb_result *results, const int32_t *label,
+                   const int32_t *kit_label, int64_t n, const char *labels, const int64_t *label_off, int32_t n_labels,
+                   int32_t trim, int64_t min_read_length, uint8_t *out, int64_t out_capacity, int64_t *out_bytes,
+                   uint8_t *kept, int32_t threads)
+{
+    if (!out_bytes) return io_fail("NULL argument");
+    *out_bytes = 0;
+    if (n == 0) return 0;
+    if (!buf || !recs || !results || !label || !kit_label || !labels || !label_off || !kept) return io_fail("NULL argument");
+    for (int64_t i = 0; i < n; ++i)
+        if (label[i] >= n_labels || kit_label[i] >= n_labels || (label[i] >= 0 && kit_label[i] < 0))
+            return io_fail("label[%lld] out of range", (long long)i);
+    threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n / 256 + 1));
+    std::vector<std::string> part((size_t)threads);
+    const int64_t step = (n + threads - 1) / threads;
+    auto work = [&](int t) {
+        std::string &dst = part[(size_t)t];
+        const int64_t lo = t * step, hi = std::min<int64_t>(n, lo + step);
+        dst.reserve((size_t)std::max<int64_t>(0, hi - lo) * 96);
+        char num[64];
+        for (int64_t i = lo; i < hi; ++i) {
+            const qcb_fastx_record &r = recs[i];
+            const Cut c = trimmed_range(r, results[i], trim);
+            const int64_t m = c.b - c.a;
+            kept[i] = m >= min_read_length ? 1 : 0;
+            if (!kept[i]) continue;
+            const char *title = buf + r.title_off;
+            int64_t name_len = r.title_len;
+            for (int64_t j = 0; j < r.title_len; ++j) if (title[j] == ' ' || title[j] == '\t') { name_len = j; break; }
+            dst.append(title, (size_t)name_len);
+            dst.push_back('\t');
+            dst.append(num, (size_t)(put_int(num, m) - num));
+            dst.push_back('\t');
+            if (label[i] >= 0) {
+                dst.append(labels + label_off[label[i]], (size_t)(label_off[label[i] + 1] - label_off[label[i]]));
+                dst.push_back('\t');
+                dst.append(num, (size_t)(put_float_repr(num, results[i].barcode_score) - num));
+                dst.push_back('\t');
+                dst.append(labels + label_off[kit_label[i]], (size_t)(label_off[kit_label[i] + 1] - label_off[kit_label[i]]));
+                dst.push_back('\t');
+                dst.append(num, (size_t)(put_int(num, results[i].adapter_end) - num));
+            } else {
+                dst.append("none\t-1\tnone\t-1");
+            }
+            dst.push_back('\t');
+            if (name_len == r.title_len) {
+                dst.append("None");
+            } else {
+                const size_t at = dst.size();
+                dst.append(title + name_len + 1, (size_t)(r.title_len - name_len - 1));
+                for (size_t j = at; j < dst.size(); ++j) if (dst[j] == '\t') dst[j] = ' ';
+            }
+            dst.push_back('\n');
+        }
+    };
+    if (threads == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+        for (auto &th : pool) th.join();
+    }
+    int64_t total = 0;
+    for (const std::string &p : part) total += (int64_t)p.size();
+    *out_bytes = total;
+    if (!out) return 0;
+    if (total > out_capacity) return io_fail("output buffer too small: need %lld bytes", (long long)total);
+    int64_t at = 0;
+    for (const std::string &p : part) { memcpy(out + at, p.data(), p.size()); at += (int64_t)p.size(); }
+    return 0;
+}
+
+// ---- chunked file reader ------------------------------------------------------------------------------------------------
+
+struct qcb_chunk {
+    qcb_reader *owner;
+    char *data;
+    int64_t capacity, len;
+    std::vector<qcb_fastx_record> recs;
+    int64_t n;
+    int32_t fastq;
+};
+
+struct qcb_reader {
+    int fd = -1;
+    int64_t file_size = 0, file_pos = 0;
+    int64_t chunk_bytes = 0;
+    int threads = 1;
+    bool eof = false;
+    qcb_chunk *pending = nullptr;            // next chunk's buffer; its first carry_len bytes follow the last record handed out
+    int64_t carry_len = 0;
+    std::vector<qcb_fastx_record> carry_recs;// records already indexed inside the carried bytes (offsets relative to their start)
+    int64_t carry_scanned = 0;               // carried bytes those records cover
+    int fastq = -1;                          // -1 until the first byte of the file has been seen
+    std::mutex pool_lock;
+    std::vector<qcb_chunk *> pool;           // released chunks, reused so their pages stay mapped
+};
+
+qcb_reader *qcb_reader_open(const char *path, int64_t chunk_bytes, int32_t threads)
+{
+    if (!path) { io_fail("NULL argument"); return nullptr; }
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { io_fail("cannot open %s", path); return nullptr; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); io_fail("cannot stat %s", path); return nullptr; }
+    qcb_reader *rd = new qcb_reader();
+    rd->fd = fd;
+    rd->file_size = (int64_t)st.st_size;
+    rd->chunk_bytes = std::max<int64_t>(chunk_bytes, 4096);
+    rd->threads = std::max(1, (int)threads);
+    return rd;
+}
+
+void qcb_reader_close(qcb_reader *rd)
+{
+    if (!rd) return;
+    if (rd->fd >= 0) close(rd->fd);
+    if (rd->pending) { free(rd->pending->data); delete rd->pending; }
+    for (qcb_chunk *c : rd->pool) { free(c->data); delete c; }
+    delete rd;
+}
+
+void qcb_chunk_release(qcb_chunk *c)
+{
+    if (!c) return;
+    qcb_reader *rd = c->owner;
+    std::lock_guard<std::mutex> g(rd->pool_lock);
+    rd->pool.push_back(c);
+}
+
+const char *qcb_chunk_data(const qcb_chunk *c, int64_t *len)
+{
+    if (len) *len = c ? c->len : 0;
+    return c ? c->data : nullptr;
+}
+
+const qcb_fastx_record *qcb_chunk_records(const qcb_chunk *c, int64_t *n, int32_t *is_fastq)
+{
+    if (n) *n = c ? c->n : 0;
+    if (is_fastq) *is_fastq = c ? c->fastq : 1;
+    return c ? c->recs.data() : nullptr;
+}
+
+namespace {
+
+// a pooled chunk whose buffer holds at least `capacity` bytes
+qcb_chunk *acquire_chunk(qcb_reader *rd, int64_t capacity)
+{
+    qcb_chunk *c = nullptr;
+    {
+        std::lock_guard<std::mutex> g(rd->pool_lock);
+        if (!rd->pool.empty()) { c = rd->pool.back(); rd->pool.pop_back(); }
+    }
+    if (!c) { c = new qcb_chunk(); c->owner = rd; c->data = nullptr; c->capacity = 0; }
+    if (c->capacity < capacity) {
+        // sized for a carried batch plus a full read, so pooled buffers (and their mapped pages) fit every later chunk
+        free(c->data);
+        c->capacity = std::max<int64_t>(capacity + capacity / 8, 2 * rd->chunk_bytes) + 4096;
+        c->data = (char *)malloc((size_t)c->capacity);
+        if (!c->data) { delete c; io_fail("out of memory"); return nullptr; }
+    }
+    return c;
+}
+
+}  // namespace
+
+// Next chunk of the file: the bytes carried over from the previous chunk followed by up to chunk_bytes new bytes (read
+// with `threads` concurrent preads), indexed in parallel.  Every chunk but the last holds a multiple of `multiple_of`
+// records (CLI batches of 4000 stay aligned across chunks); the records kept back travel on, already indexed, at the
+// front of the next chunk's buffer.  *chunk = NULL at the end of the file.
+int qcb_reader_next(qcb_reader *rd, int64_t multiple_of, qcb_chunk **chunk)
+{
+    if (!rd || !chunk) return io_fail("NULL argument");
+    *chunk = nullptr;
+    if (multiple_of < 1) multiple_of = 1;
+    for (;;) {
+        if (rd->eof && rd->carry_len == 0) return 0;
+        const int64_t want = std::min<int64_t>(rd->chunk_bytes, rd->file_size - rd->file_pos);
+        const int64_t total = rd->carry_len + want;
+        auto T0 = std::chrono::steady_clock::now();
+        qcb_chunk *c = rd->pending;
+        rd->pending = nullptr;
+        if (!c || c->capacity < total + 1) {
+            qcb_chunk *bigger = acquire_chunk(rd, total + 1);
+            if (!bigger) { if (c) qcb_chunk_release(c); return 1; }
+            if (c) { memcpy(bigger->data, c->data, (size_t)rd->carry_len); qcb_chunk_release(c); }
+            c = bigger;
+        }
+        char *dst = c->data + rd->carry_len;
+        std::vector<int64_t> got((size_t)rd->threads, 0);
+        {
+            const int64_t base = rd->file_pos;
+            const int fd = rd->fd;
+            int64_t *gp = got.data();
+            const int T = rd->threads;
+            const int64_t step = (want + T - 1) / std::max(T, 1);
+            auto reader = [=](int t) {
+                int64_t lo = t * step, hi = std::min<int64_t>(want, lo + step);
+                while (lo < hi) {
+                    const ssize_t k = pread(fd, dst + lo, (size_t)(hi - lo), (off_t)(base + lo));
+                    if (k <= 0) break;
+                    lo += k;
+                    gp[t] += k;
+                }
+            };
+            if (T == 1 || want < (1 << 20)) { for (int t = 0; t < T; ++t) reader(t); }
+            else {
+                std::vector<std::thread> pool;
+                for (int t = 0; t < T; ++t) pool.emplace_back(reader, t);
+                for (auto &th : pool) th.join();
+            }
+        }
+        auto T1 = std::chrono::steady_clock::now();
+        int64_t nread = 0;
+        for (int64_t g : got) nread += g;
+        if (nread != want) { qcb_chunk_release(c); rd->carry_len = 0; return io_fail("short read"); }
+        rd->file_pos += want;
+        if (rd->file_pos >= rd->file_size) rd->eof = true;
+        const bool final_chunk = rd->eof;
+        if (rd->fastq < 0) {
+            const char *p0 = c->data, *e0 = c->data + total;
+            while (p0 < e0 && (*p0 == '\n' || *p0 == '\r')) ++p0;
+            if (p0 < e0) {
+                if (*p0 != '@' && *p0 != '>') {
+                    qcb_chunk_release(c);
+                    return io_fail("Invalid input file. File must start with '@' or '>'. Current file starts with: %c", *p0);
+                }
+                rd->fastq = *p0 == '@' ? 1 : 0;
+            }
+        }
+        const int32_t fastq = rd->fastq < 0 ? 1 : rd->fastq;
+        // Records of the carried bytes were indexed last time; scan only what follows them, with a record array that
+        // grows until the scan is no longer limited by it.
+        const int64_t n0 = (int64_t)rd->carry_recs.size();
+        int64_t cap = std::max<int64_t>(4096, (total - rd->carry_scanned) / 512), n = 0, consumed = rd->carry_scanned;
+        for (;;) {
+            c->recs.resize((size_t)(n0 + cap));
+            const char *done = c->data + rd->carry_scanned;
+            int64_t got_n = 0;
+            const int rc = index_from(c->data, done, c->data + total, fastq != 0, final_chunk, rd->threads,
+                                      c->recs.data() + n0, cap, &got_n, &done);
+            if (rc != 0) { qcb_chunk_release(c); rd->carry_len = 0; return rc; }
+            n = n0 + got_n;
+            consumed = done - c->data;
+            if (got_n < cap) break;
+            cap *= 4;
+        }
+        auto T2 = std::chrono::steady_clock::now();
+        if (n0) memcpy(c->recs.data(), rd->carry_recs.data(), (size_t)n0 * sizeof(qcb_fastx_record));
+        int64_t keep = n;
+        if (!final_chunk && n % multiple_of) keep = n - n % multiple_of;
+        // bytes handed out end where the first record kept back starts; those records travel on with their bytes
+        const int64_t cut = keep < n ? c->recs[(size_t)keep].title_off - 1 : consumed;
+        if (final_chunk) {
+            for (const char *q = c->data + cut; q < c->data + total; ++q)
+                if (!(*q == '\n' || *q == '\r' || *q == ' ' || *q == '\t')) { qcb_chunk_release(c); rd->carry_len = 0; return io_fail("trailing bytes that do not form a record"); }
+            rd->carry_recs.clear();
+            rd->carry_scanned = 0;
+            rd->carry_len = 0;
+        } else {
+            rd->carry_recs.assign(c->recs.begin() + keep, c->recs.begin() + n);
+            for (qcb_fastx_record &r : rd->carry_recs) {
+                r.title_off -= cut; r.seq_off -= cut;
+                if (r.qual_off >= 0) r.qual_off -= cut;
+            }
+            rd->carry_scanned = consumed - cut;
+            rd->carry_len = total - cut;
+            if (rd->carry_len > 64 * rd->chunk_bytes) { qcb_chunk_release(c); rd->carry_len = 0; return io_fail("record larger than 64 chunks"); }
+            if (keep == 0) {                                          // nothing to hand out yet: keep reading into this buffer
+                rd->pending = c;
+                continue;
+            }
+            qcb_chunk *next = acquire_chunk(rd, rd->carry_len + std::min<int64_t>(rd->chunk_bytes, rd->file_size - rd->file_pos) + 1);
+            if (!next) { qcb_chunk_release(c); rd->carry_len = 0; return 1; }
+            memcpy(next->data, c->data + cut, (size_t)rd->carry_len);
+            rd->pending = next;
+        }
+        auto T3 = std::chrono::steady_clock::now();
+        if (getenv("QCB_IO_TRACE")) fprintf(stderr, "read %.1f ms  index %.1f ms  carry %.1f ms  (total %lld carry %lld)\n",
+            std::chrono::duration<double, std::milli>(T1 - T0).count(), std::chrono::duration<double, std::milli>(T2 - T1).count(),
+            std::chrono::duration<double, std::milli>(T3 - T2).count(), (long long)total, (long long)rd->carry_len);
+        c->len = cut;
+        c->n = keep;
+        c->fastq = fastq;
+        if (keep == 0) { qcb_chunk_release(c); return 0; }            // final chunk without records
+        *chunk = c;
+        return 0;
+    }
 }
 
 }  // extern "C"

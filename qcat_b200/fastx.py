@@ -1,13 +1,19 @@
-"""Native FASTQ / FASTA ingest and per-barcode output around the hot path.
+"""Native FASTQ / FASTA ingest and output around the hot path.
 
 Mirrors what `qcat/cli.py` does around `detect_barcode_batch` -- `iter_fastx` (cli.py:235-306), trimming and the
-min-length filter (:521-530), the TSV lines (:408-442) and the per-barcode files of `-b` (:309-358) -- but on memory
-buffers: records are indexed and cut into windows by libqcat_b200.so (`qcb_fastx_index`, `qcb_pack_windows`), scored
-in batches of `batch_size` reads exactly like the CLI (the kit vote is per batch), and written through
-`qcb_format_records`.  Strings are only materialised for the TSV.
+min-length filter (:521-530), the TSV lines (:408-442), the per-barcode files of `-b` (:309-336) and the single
+output stream with `barcode=<id>` comments (:337-352) -- but on memory buffers: chunks of the file are read and
+indexed by several threads inside libqcat_b200.so (`qcb_reader_*`, `qcb_fastx_index_mt`), cut into windows
+(`qcb_pack_windows`), scored in batches of `batch_size` reads exactly like the CLI (the kit vote is per batch), and
+written through `qcb_format_records` / `qcb_format_stream` / `qcb_format_tsv`.  `demux_file` runs the three stages
+(read + index + pack, device scoring, format + write) as a pipeline on three threads; the native calls release
+the GIL.  No Python string is created per read.
 """
 import ctypes
+import io
 import os
+import queue
+import threading
 
 import numpy as np
 
@@ -28,8 +34,12 @@ def _check_io(rc):
         raise FastxError(msg.decode("utf-8", "replace") if msg else "fastx error")
 
 
-def index_buffer(buf, final_chunk=True, max_records=None):
-    """Index the complete records of a bytes-like FASTQ / FASTA chunk.
+def _threads(threads):
+    return int(threads or os.cpu_count() or 1)
+
+
+def index_buffer(buf, final_chunk=True, max_records=None, threads=1):
+    """Index the complete records of a bytes-like FASTQ / FASTA chunk (threads > 1: parallel scan, same result).
     Returns (records structured array, bytes consumed, is_fastq)."""
     lib = _ffi.load()
     arr = np.frombuffer(buf, dtype=np.uint8)
@@ -39,16 +49,16 @@ def index_buffer(buf, final_chunk=True, max_records=None):
     n = ctypes.c_int64(0)
     consumed = ctypes.c_int64(0)
     fastq = ctypes.c_int32(1)
-    _check_io(lib.qcb_fastx_index(_vp(arr) if arr.size else None, int(arr.size), 1 if final_chunk else 0, _vp(recs),
-                                  int(max_records), ctypes.byref(n), ctypes.byref(consumed), ctypes.byref(fastq))
-              if arr.size else 0)
+    if arr.size:
+        _check_io(lib.qcb_fastx_index_mt(_vp(arr), int(arr.size), 1 if final_chunk else 0, _vp(recs), int(max_records),
+                                         ctypes.byref(n), ctypes.byref(consumed), ctypes.byref(fastq), int(threads)))
     return recs[:n.value], int(consumed.value), bool(fastq.value)
 
 
 def pack_windows(buf, recs, max_align_length=150, threads=None):
     """(win5, tail3, wlen, read_len) of indexed records -- the buffers DevicePlan.detect takes."""
     lib = _ffi.load()
-    arr = np.frombuffer(buf, dtype=np.uint8)
+    arr = buf if isinstance(buf, np.ndarray) else np.frombuffer(buf, dtype=np.uint8)
     n = len(recs)
     W = int(max_align_length)
     stride = max(16, (W + 15) // 16 * 16)
@@ -59,13 +69,14 @@ def pack_windows(buf, recs, max_align_length=150, threads=None):
     recs = np.ascontiguousarray(recs)
     if n:
         _check_io(lib.qcb_pack_windows(_vp(arr), _vp(recs), n, W, stride, _vp(win5), _vp(tail3), _vp(wlen), _vp(read_len),
-                                       threads or os.cpu_count() or 1))
+                                       _threads(threads)))
     return win5, tail3, wlen, read_len
 
 
-def iter_chunks(path, chunk_bytes=64 << 20, multiple_of=1):
+def iter_chunks(path, chunk_bytes=64 << 20, multiple_of=1, threads=1):
     """Yield (buffer, records, is_fastq) for consecutive chunks of a FASTQ / FASTA file; records never straddle chunks
-    and every chunk but the last holds a multiple of `multiple_of` records (so CLI batches of 4000 stay aligned)."""
+    and every chunk but the last holds a multiple of `multiple_of` records (so CLI batches of 4000 stay aligned).
+    Pure-Python chunking over `index_buffer`; `Reader` is the native equivalent demux_file uses."""
     carry = b""
     with open(path, "rb") as fh:
         while True:
@@ -74,7 +85,7 @@ def iter_chunks(path, chunk_bytes=64 << 20, multiple_of=1):
             buf = carry + block
             if not buf:
                 return
-            recs, consumed, fastq = index_buffer(buf, final_chunk=final)
+            recs, consumed, fastq = index_buffer(buf, final_chunk=final, threads=threads)
             if not final and multiple_of > 1:
                 keep = (len(recs) // multiple_of) * multiple_of
                 if keep < len(recs):
@@ -89,128 +100,378 @@ def iter_chunks(path, chunk_bytes=64 << 20, multiple_of=1):
                 return
 
 
-def _title(buf, rec):
-    header = bytes(buf[int(rec["title_off"]):int(rec["title_off"] + rec["title_len"])]).decode("latin-1")
-    cols = header.replace("\t", " ").split(" ")                  # extract_fastx_comment, cli.py:199-213
-    return cols[0], (" ".join(cols[1:]) if len(cols) > 1 else None)
+class Chunk(object):
+    """One chunk of complete records owned by the native reader: `.data` (uint8 view of the bytes), `.recs`
+    (structured view of the record index), `.fastq`.  Views die with release()."""
+
+    def __init__(self, lib, handle):
+        self._lib, self._handle = lib, handle
+        length = ctypes.c_int64(0)
+        n = ctypes.c_int64(0)
+        fastq = ctypes.c_int32(1)
+        data = lib.qcb_chunk_data(handle, ctypes.byref(length))
+        recs = lib.qcb_chunk_records(handle, ctypes.byref(n), ctypes.byref(fastq))
+        self.data = np.ctypeslib.as_array(ctypes.cast(data, ctypes.POINTER(ctypes.c_uint8)), shape=(length.value,))
+        raw = np.ctypeslib.as_array(ctypes.cast(recs, ctypes.POINTER(ctypes.c_uint8)),
+                                    shape=(n.value * _ffi.RECORD_DTYPE.itemsize,)) if n.value else np.zeros(0, np.uint8)
+        self.recs = raw.view(_ffi.RECORD_DTYPE)
+        self.fastq = bool(fastq.value)
+
+    def __len__(self):
+        return len(self.recs)
+
+    def release(self):
+        if self._handle:
+            self._lib.qcb_chunk_release(self._handle)
+            self._handle = None
+            self.data = self.recs = None
 
 
-def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min_read_length=0, out_dir=None, tsv=None,
-               nobatch=False, chunk_bytes=64 << 20):
-    """Demultiplex a FASTQ / FASTA file like `qcat -f path [-b out_dir] [--tsv] [--trim]` (cli.py:445-563).
+class Reader(object):
+    """Native chunked FASTQ / FASTA reader (qcb_reader_*): parallel pread + parallel record scan per chunk."""
 
-    scanner: a qcat_b200 (or drop-in patched qcat) scanner.  Reads are scored in batches of `batch_size` (4000 in the
-    CLI; `nobatch` = single-read mode without the kit vote).  out_dir: per-barcode files as with `-b`; tsv: a text
-    file object receiving the `--tsv` table.  Returns {"reads", "skipped", "barcodes": {name: count}, "records"}.
-    """
-    from qcat_b200 import scanner as qscanner
-    qcat_config = qcat_config or qscanner._default_config()
-    lib = _ffi.load()
-    plan = scanner._plan_for(qcat_config)
+    def __init__(self, path, chunk_bytes=64 << 20, threads=None):
+        self._lib = _ffi.load()
+        self._handle = self._lib.qcb_reader_open(os.fsencode(path), int(chunk_bytes), _threads(threads))
+        if not self._handle:
+            msg = self._lib.qcb_io_last_error()
+            raise IOError(msg.decode("utf-8", "replace") if msg else "cannot open %s" % path)
+
+    def next_chunk(self, multiple_of=1):
+        """The next Chunk, or None at the end of the file."""
+        handle = ctypes.c_void_p(None)
+        _check_io(self._lib.qcb_reader_next(self._handle, int(multiple_of), ctypes.byref(handle)))
+        return Chunk(self._lib, handle.value) if handle.value else None
+
+    def chunks(self, multiple_of=1):
+        while True:
+            chunk = self.next_chunk(multiple_of)
+            if chunk is None:
+                return
+            yield chunk
+
+    def close(self):
+        if self._handle:
+            self._lib.qcb_reader_close(self._handle)
+            self._handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class _Labels(object):
+    """Strings the writers need per record, interned: output bin (barcode name), barcode id, kit."""
+
+    def __init__(self, tables):
+        self.tables = tables
+        self.strings = []
+        self.index = {}
+        self.none = self.intern("none")
+        self.by_key = {}                      # (layout << 32 | barcode) -> (name label, id label, kit label)
+
+    def intern(self, text):
+        if text not in self.index:
+            self.index[text] = len(self.strings)
+            self.strings.append(text)
+        return self.index[text]
+
+    def lookup(self, key):
+        if key not in self.by_key:
+            layout_index, barcode_index = int(key >> 32), int(key & 0xffffffff)
+            b = self.tables.barcode_object(layout_index, barcode_index)
+            if self.tables.mode == 1:           # dual: names and ids are synthesised per pair (scanner_dual.py:132-136)
+                name, bid = "barcode{:02d}/{:02d}".format(b[0].id, b[1].id), "{}/{}".format(b[0].id, b[1].id)
+            else:
+                name, bid = b.name, str(b.id)
+            self.by_key[key] = (self.intern(name), self.intern(bid), self.intern(str(self.tables.layouts[layout_index].kit)))
+        return self.by_key[key]
+
+    def table(self):
+        blobs = [s.encode("latin-1") for s in self.strings]
+        off = np.zeros(len(blobs) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(b) for b in blobs])
+        return np.frombuffer(b"".join(blobs) + b"\0", dtype=np.uint8), off
+
+
+def _batch_kits(vote, kit_of_layout, n_kits, batch_size):
+    """Per CLI batch: the kit named by most reads' best-scoring end; ties go to the kit seen first in the batch
+    (detect_kit / get_most_abundant_kits, scanner_base.py:657-678: dict insertion order + stable sort)."""
+    kits = []
+    v = kit_of_layout[vote]
+    for lo in range(0, len(v), batch_size):
+        part = v[lo:lo + batch_size]
+        counts = np.bincount(part, minlength=n_kits)
+        best = np.nonzero(counts == counts.max())[0]
+        if len(best) > 1:
+            first = [int(np.argmax(part == k)) for k in best]
+            best = [best[int(np.argmin(first))]]
+        kits.append(int(best[0]))
+    return kits
+
+
+def _score_chunk(scanner, plan, packed, batch_size, nobatch):
+    """qcb_result records of one chunk, batch semantics of the CLI loop (cli.py:500-513)."""
+    win5, tail3, wlen, read_len = packed
     tables = plan.tables
-    threads = os.cpu_count() or 1
-    files = {}
-    counts = {}
-    all_records = []
-    total = skipped = 0
-    if tsv is not None:
-        print("name", "length", "barcode", "score", "kit", "adapter_end", "comment", sep="\t", file=tsv)
-    if out_dir:
-        os.makedirs(out_dir, exist_ok=True)
+    n = len(wlen)
+    results = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+    names = [layout.kit for layout in scanner.layouts]
+    kit_names = list(dict.fromkeys(names))
+    if nobatch or len(kit_names) == 1:
+        # no vote needed (single-read mode, or every layout names the same kit): one device call per chunk
+        plan.detect(win5, tail3, wlen, read_len, scanner._subset_for(plan, scanner.layouts), out=results)
+    else:
+        vote = plan.kit_vote(win5, tail3, wlen)                 # one device call for the whole chunk
+        kit_of_layout = np.array([kit_names.index(k) for k in names], dtype=np.int64)
+        kits = _batch_kits(vote, kit_of_layout, len(kit_names), batch_size)
+        b = 0
+        while b < len(kits):                                    # consecutive batches that chose the same kit: one call
+            e = b
+            while e + 1 < len(kits) and kits[e + 1] == kits[b]:
+                e += 1
+            lo, hi = b * batch_size, min(n, (e + 1) * batch_size)
+            plan.detect(win5[lo:hi], tail3[lo:hi], wlen[lo:hi], read_len[lo:hi], tables.kit_subset(kit_names[kits[b]]),
+                        out=results[lo:hi])
+            b = e + 1
+    if getattr(scanner, "enable_filter_barcodes", False) and not nobatch:
+        _filter_barcodes(tables, results, batch_size)
+    return results
 
-    # output bins: 0 = none, then one per distinct barcode name seen (dual: names are synthesised per pair)
-    bin_names = ["none"]
-    bin_of_name = {"none": 0}
 
-    for buf, recs, fastq in iter_chunks(path, chunk_bytes, multiple_of=1 if nobatch else batch_size):
-        arr = np.frombuffer(buf, dtype=np.uint8)
-        win5, tail3, wlen, read_len = pack_windows(buf, recs, qcat_config.max_align_length, threads)
-        n = len(recs)
-        results = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
-        names = [layout.kit for layout in scanner.layouts]
-        step = 1 if nobatch else batch_size
-        if nobatch or len(set(names)) == 1:
-            # no vote needed (single read mode, or every layout names the same kit): one device call per chunk
-            kits = scanner.layouts
-            subset = scanner._subset_for(plan, kits)
-            plan.detect(win5, tail3, wlen, read_len, subset, out=results)
+def _filter_barcodes(tables, results, batch_size):
+    """filter_barcodes per CLI batch (scanner_base.py:680-712): barcode ids seen in <= int(5 % of the most frequent
+    key's count) reads -- "0" = unclassified counts as a key -- become empty results (trims reset to 0)."""
+    n = len(results)
+    called = (results["layout"] >= 0) & (results["barcode"] >= 0)
+    key = results["layout"].astype(np.int64) * (1 << 32) + results["barcode"].astype(np.int64)
+    ids = np.zeros(n, dtype=np.int64)                           # 0 = unclassified (barcode ids start at 1)
+    uniq, inverse = np.unique(key[called], return_inverse=True)
+    id_of = {}
+    codes = np.zeros(len(uniq), dtype=np.int64)
+    for j, k in enumerate(uniq):
+        b = tables.barcode_object(int(k >> 32), int(k & 0xffffffff))
+        ident = (b[0].id, b[1].id) if tables.mode == 1 else b.id
+        codes[j] = id_of.setdefault(ident, len(id_of) + 1)
+    ids[called] = codes[inverse]
+    for lo in range(0, n, batch_size):
+        part = ids[lo:lo + batch_size]
+        counts = np.bincount(part)
+        min_count = int(counts.max() * 0.05)
+        drop = (counts[part] <= min_count) & (part > 0)
+        if drop.any():
+            view = results[lo:lo + batch_size]
+            view[drop] = np.array((-1, -1, 0.0, 0, 0, 0, 1), dtype=_ffi.RESULT_DTYPE)
+
+
+class _Writer(object):
+    """Formats and writes one chunk's records; keeps the running counts."""
+
+    def __init__(self, plan, trim, min_read_length, out_dir, tsv, output, threads):
+        self.lib = _ffi.load()
+        self.tables = plan.tables
+        self.labels = _Labels(plan.tables)
+        self.trim, self.min_read_length = bool(trim), int(min_read_length)
+        self.out_dir, self.tsv, self.output = out_dir, tsv, output
+        self.threads = threads
+        self.files = {}
+        self.counts = {}
+        self.kit_counts = {}
+        self.total = self.skipped = 0
+        self._own_output = None
+        if out_dir:
+            os.makedirs(out_dir, exist_ok=True)
+        if isinstance(output, (str, bytes, os.PathLike)):
+            self._own_output = self.output = open(output, "wb")
+        if tsv is not None:
+            self._write(tsv, b"name\tlength\tbarcode\tscore\tkit\tadapter_end\tcomment\n")
+
+    @staticmethod
+    def _write(fh, data):
+        if isinstance(fh, io.TextIOBase):
+            fh.write(bytes(data).decode("latin-1"))
         else:
-            for lo in range(0, n, step):
-                hi = min(n, lo + step)
-                vote = plan.kit_vote(win5[lo:hi], tail3[lo:hi], wlen[lo:hi])
-                kit = scanner._kit_from_votes(vote, names)
-                subset = tables.kit_subset(kit)
-                plan.detect(win5[lo:hi], tail3[lo:hi], wlen[lo:hi], read_len[lo:hi], subset, out=results[lo:hi])
-        if getattr(scanner, "enable_filter_barcodes", False) and not nobatch:
-            for lo in range(0, n, step):                           # filter_barcodes works per CLI batch
-                hi = min(n, lo + step)
-                dicts = [scanner._record_to_dict(plan, r) for r in results[lo:hi]]
-                count = {}
-                for d in dicts:
-                    scanner.update_barcode_count(d, count)
-                valid = scanner.get_valid(count, 0.05)
-                for i, d in enumerate(dicts):
-                    if d["barcode"] and d["barcode"].id not in valid:
-                        results[lo + i] = (-1, -1, 0.0, 0, results[lo + i]["trim5p"], results[lo + i]["trim3p"], 1)
-        all_records.append(results)
+            fh.write(data)
 
-        # barcode name per record (vectorised through a small lookup over the distinct (layout, barcode) pairs)
-        key = results["layout"].astype(np.int64) * (1 << 32) + results["barcode"].astype(np.int64)
+    def emit(self, chunk, read_len, results):
+        n = len(results)
+        labels = self.labels
         called = (results["layout"] >= 0) & (results["barcode"] >= 0)
-        bins = np.zeros(n, dtype=np.int32)
-        for k in np.unique(key[called]):
-            layout_index, barcode_index = int(k >> 32), int(k & 0xffffffff)
-            b = tables.barcode_object(layout_index, barcode_index)
-            name = "barcode{:02d}/{:02d}".format(b[0].id, b[1].id) if tables.mode == 1 else b.name
-            if name not in bin_of_name:
-                bin_of_name[name] = len(bin_names)
-                bin_names.append(name)
-            bins[called & (key == k)] = bin_of_name[name]
+        key = results["layout"].astype(np.int64) * (1 << 32) + results["barcode"].astype(np.int64)
+        name_label = np.full(n, labels.none, dtype=np.int32)
+        id_label = np.full(n, labels.none, dtype=np.int32)
+        kit_label = np.full(n, labels.none, dtype=np.int32)
+        uniq, inverse = np.unique(key[called], return_inverse=True)
+        if len(uniq):
+            trip = np.array([labels.lookup(int(k)) for k in uniq], dtype=np.int32).reshape(-1, 3)
+            name_label[called], id_label[called], kit_label[called] = trip[inverse, 0], trip[inverse, 1], trip[inverse, 2]
+        # adapter histogram key (cli.py:369-377): the kit of the detected adapter, also for reads without a barcode
+        with_adapter = results["layout"] >= 0
+        strings = labels.strings
 
-        # lengths after trimming and the min-length filter (cli.py:521-530)
-        if trim:
+        if self.trim:
             a = np.clip(results["trim5p"].astype(np.int64), 0, read_len)
             b = np.maximum(np.clip(results["trim3p"].astype(np.int64), 0, read_len), a)
             out_len = b - a
         else:
             out_len = read_len
-        kept = out_len >= min_read_length
-        total += n
-        skipped += int((~kept).sum())
-        for b_index, cnt in zip(*np.unique(bins[kept], return_counts=True)):
-            counts[bin_names[b_index]] = counts.get(bin_names[b_index], 0) + int(cnt)
+        kept = out_len >= self.min_read_length
+        self.total += n
+        self.skipped += int((~kept).sum())
+        for index, cnt in zip(*np.unique(name_label[kept], return_counts=True)):
+            self.counts[strings[index]] = self.counts.get(strings[index], 0) + int(cnt)
+        kit_of_layout = [str(layout.kit) for layout in self.tables.layouts]
+        for index, cnt in zip(*np.unique(results["layout"][kept & with_adapter], return_counts=True)):
+            self.kit_counts[kit_of_layout[index]] = self.kit_counts.get(kit_of_layout[index], 0) + int(cnt)
+        no_adapter = int((kept & ~with_adapter).sum())
+        if no_adapter:
+            self.kit_counts["none"] = self.kit_counts.get("none", 0) + no_adapter
 
-        if tsv is not None:
-            for i in np.nonzero(kept)[0]:
-                name, comment = _title(arr, recs[i])
-                r = results[i]
-                if bins[i]:
-                    b = tables.barcode_object(int(r["layout"]), int(r["barcode"]))
-                    bid = "{}/{}".format(b[0].id, b[1].id) if tables.mode == 1 else b.id
-                    print(name, int(out_len[i]), bid, float(r["barcode_score"]), tables.layouts[int(r["layout"])].kit,
-                          int(r["adapter_end"]), comment, sep="\t", file=tsv)
-                else:
-                    print(name, int(out_len[i]), "none", "-1", "none", "-1", comment, sep="\t", file=tsv)
-
-        if out_dir:
-            n_bins = len(bin_names)
+        if not (self.tsv is not None or self.out_dir or self.output is not None):
+            return
+        lib = self.lib
+        recs = np.ascontiguousarray(chunk.recs)
+        results = np.ascontiguousarray(results)
+        blob, off = labels.table()
+        kept_u8 = np.zeros(n, dtype=np.uint8)
+        need = ctypes.c_int64(0)
+        if self.tsv is not None:
+            tsv_label = np.where(called, id_label, -1).astype(np.int32)
+            cap = int(recs["title_len"].sum()) + 160 * n + 64
+            out = np.empty(cap, dtype=np.uint8)
+            _check_io(lib.qcb_format_tsv(_vp(chunk.data), _vp(recs), _vp(results), _vp(tsv_label), _vp(kit_label), n, _vp(blob),
+                                         _vp(off), len(strings), 1 if self.trim else 0, self.min_read_length, _vp(out), cap,
+                                         ctypes.byref(need), _vp(kept_u8), self.threads))
+            self._write(self.tsv, out[:need.value].data)
+        if self.out_dir:
+            n_bins = len(strings)
             bin_bytes = np.zeros(n_bins, dtype=np.int64)
             bin_off = np.zeros(n_bins, dtype=np.int64)
-            kept_u8 = np.zeros(n, dtype=np.uint8)
-            recs_c = np.ascontiguousarray(recs)
-            args = (_vp(arr), _vp(recs_c), _vp(results), _vp(bins), n, n_bins, 1 if fastq else 0, 1 if trim else 0,
-                    int(min_read_length), _vp(bin_bytes))
-            _check_io(lib.qcb_format_records(*args, None, 0, _vp(bin_off), _vp(kept_u8), threads))
+            args = (_vp(chunk.data), _vp(recs), _vp(results), _vp(name_label), n, n_bins, 1 if chunk.fastq else 0,
+                    1 if self.trim else 0, self.min_read_length, _vp(bin_bytes))
+            _check_io(lib.qcb_format_records(*args, None, 0, _vp(bin_off), _vp(kept_u8), self.threads))
             out = np.empty(int(bin_bytes.sum()) + 1, dtype=np.uint8)
-            _check_io(lib.qcb_format_records(*args, _vp(out), int(out.size), _vp(bin_off), _vp(kept_u8), threads))
-            for b_index in range(n_bins):
-                if bin_bytes[b_index] == 0:
-                    continue
-                name = bin_names[b_index].replace("/", "_")
-                if name not in files:
-                    files[name] = open(os.path.join(out_dir, name + (".fastq" if fastq else ".fasta")), "wb")
-                files[name].write(out[bin_off[b_index]:bin_off[b_index] + bin_bytes[b_index]].tobytes())
-    for fh in files.values():
-        fh.close()
+            _check_io(lib.qcb_format_records(*args, _vp(out), int(out.size), _vp(bin_off), _vp(kept_u8), self.threads))
+            for index in np.nonzero(bin_bytes)[0]:
+                name = strings[index].replace("/", "_")
+                if name not in self.files:
+                    self.files[name] = open(os.path.join(self.out_dir, name + (".fastq" if chunk.fastq else ".fasta")), "wb")
+                self.files[name].write(out[bin_off[index]:bin_off[index] + bin_bytes[index]].data)
+        elif self.output is not None:
+            # cli.py:552: the single stream is written when there is no -b folder
+            args = (_vp(chunk.data), _vp(recs), _vp(results), _vp(id_label), n, _vp(blob), _vp(off), len(strings),
+                    1 if chunk.fastq else 0, 1 if self.trim else 0, self.min_read_length)
+            _check_io(lib.qcb_format_stream(*args, None, 0, ctypes.byref(need), _vp(kept_u8), self.threads))
+            out = np.empty(need.value + 1, dtype=np.uint8)
+            _check_io(lib.qcb_format_stream(*args, _vp(out), int(out.size), ctypes.byref(need), _vp(kept_u8), self.threads))
+            self._write(self.output, out[:need.value].data)
+
+    def close(self):
+        for fh in self.files.values():
+            fh.close()
+        if self._own_output is not None:
+            self._own_output.close()
+
+
+_STOP = object()
+
+
+def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min_read_length=0, out_dir=None, tsv=None,
+               output=None, nobatch=False, chunk_bytes=None, threads=None, keep_records=True):
+    """Demultiplex a FASTQ / FASTA file like `qcat -f path [-b out_dir] [--tsv] [-o output] [--trim]` (cli.py:445-563).
+
+    scanner: a qcat_b200 (or drop-in patched qcat) scanner.  Reads are scored in batches of `batch_size` (4000 in the
+    CLI; `nobatch` = single-read mode without the kit vote).  out_dir: per-barcode files as with `-b`; tsv: a file
+    object receiving the `--tsv` table; output: path or file object for the CLI's single output stream (records with
+    `barcode=<id>` comments; written when out_dir is not given, like the CLI).  Returns {"reads", "skipped",
+    "barcodes": {name: count}, "kits": {kit: count}, "records"} (records = all qcb_result rows unless
+    keep_records=False).
+
+    Three pipeline stages on three threads: (1) native read + parallel index + window packing of chunk k+1, (2) device
+    scoring of chunk k, (3) native formatting + file writes of chunk k-1.
+    """
+    from qcat_b200 import scanner as qscanner
+    qcat_config = qcat_config or qscanner._default_config()
+    plan = scanner._plan_for(qcat_config)
+    threads = _threads(threads)
+    writer = _Writer(plan, trim, min_read_length, out_dir, tsv, output, threads)
+    all_records = []
+    packed_q = queue.Queue(maxsize=2)
+    scored_q = queue.Queue(maxsize=2)
+    failure = []
+    # batches only matter when there is a kit vote or a per-batch barcode filter; chunks aligned to batches carry up to
+    # one batch of bytes from chunk to chunk, so they are made larger
+    batched = not nobatch and (len(set(l.kit for l in scanner.layouts)) > 1 or getattr(scanner, "enable_filter_barcodes", False))
+    multiple_of = batch_size if batched else 1
+    if chunk_bytes is None:
+        chunk_bytes = (256 << 20) if batched else (64 << 20)
+
+    def produce():
+        try:
+            with Reader(path, chunk_bytes, threads) as reader:
+                for chunk in reader.chunks(multiple_of):
+                    if failure:
+                        chunk.release()
+                        break
+                    packed = pack_windows(chunk.data, chunk.recs, qcat_config.max_align_length, threads)
+                    packed_q.put((chunk, packed))
+                    # the reader outlives its chunks: wait for the consumer before closing it
+                packed_q.put(_STOP)
+                done.wait()
+        except BaseException as exc:                           # noqa: BLE001 -- re-raised on the caller's thread
+            failure.append(exc)
+            packed_q.put(_STOP)
+
+    def consume():
+        try:
+            while True:
+                item = scored_q.get()
+                if item is _STOP:
+                    return
+                chunk, read_len, results = item
+                try:
+                    if not failure:
+                        writer.emit(chunk, read_len, results)
+                finally:
+                    chunk.release()
+        except BaseException as exc:                           # noqa: BLE001
+            failure.append(exc)
+            while scored_q.get() is not _STOP:                 # drain so the scoring thread never blocks
+                pass
+
+    done = threading.Event()
+    producer = threading.Thread(target=produce, name="qcb-ingest", daemon=True)
+    consumer = threading.Thread(target=consume, name="qcb-egress", daemon=True)
+    producer.start()
+    consumer.start()
+    try:
+        while True:
+            item = packed_q.get()
+            if item is _STOP:
+                break
+            chunk, packed = item
+            if failure:
+                chunk.release()
+                continue
+            try:
+                results = _score_chunk(scanner, plan, packed, batch_size, nobatch)
+            except BaseException as exc:                       # noqa: BLE001
+                failure.append(exc)
+                chunk.release()
+                continue
+            if keep_records:
+                all_records.append(results)
+            scored_q.put((chunk, packed[3], results))
+    finally:
+        scored_q.put(_STOP)
+        consumer.join()
+        done.set()
+        producer.join()
+        writer.close()
+    if failure:
+        raise failure[0]
     records = np.concatenate(all_records) if all_records else np.zeros(0, dtype=_ffi.RESULT_DTYPE)
-    return {"reads": total, "skipped": skipped, "barcodes": counts, "records": records}
+    return {"reads": writer.total, "skipped": writer.skipped, "barcodes": writer.counts, "kits": writer.kit_counts,
+            "records": records}

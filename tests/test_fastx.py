@@ -127,3 +127,157 @@ def test_format_records_matches_cli_layout():
                 print("@" + name + " " + (comment or ""), seq, "+", qual or "", sep="\n", file=want)
             got = out[bin_off[b]:bin_off[b] + bin_bytes[b]].tobytes().decode()
             assert got == want.getvalue()
+
+
+def _big_reads(n, seed, qual_alphabet):
+    rng = random.Random(seed)
+    reads = []
+    for i in range(n):
+        length = rng.randint(0, 3) if i % 97 == 0 else rng.randint(200, 2400)
+        seq = "".join(rng.choices("ACGT", k=length))
+        qual = "".join(rng.choices(qual_alphabet, k=length))
+        reads.append(("r%d ch=%d" % (i, i % 512), seq, qual))
+    return reads
+
+
+def test_parallel_index_equals_serial_scan():
+    """qcb_fastx_index_mt cuts the buffer at record starts it can verify; quality lines that start with '@' or '+'
+    (the classic FASTQ ambiguity) must not fool it, and wrapped FASTQ must fall back to the serial scan."""
+    reads = _big_reads(2500, 9, "@+I5#")                              # ~3.3 MB, every 5th quality line starts with '@' / '+'
+    buf = _fastq_bytes(reads)
+    assert len(buf) > (2 << 20)
+    serial, consumed_s, _ = fastx.index_buffer(buf, threads=1)
+    for threads in (2, 3, 8):
+        par, consumed_p, is_fastq = fastx.index_buffer(buf, threads=threads)
+        assert is_fastq and consumed_p == consumed_s == len(buf)
+        assert len(par) == len(reads) and par.tobytes() == serial.tobytes()
+    # not the end of the input: the incomplete last record stays unconsumed in both scans
+    cutoff = len(buf) - 700
+    serial, consumed_s, _ = fastx.index_buffer(buf[:cutoff], final_chunk=False, threads=1)
+    par, consumed_p, _ = fastx.index_buffer(buf[:cutoff], final_chunk=False, threads=8)
+    assert consumed_p == consumed_s < cutoff and par.tobytes() == serial.tobytes()
+    # max_records smaller than the buffer holds
+    serial, consumed_s, _ = fastx.index_buffer(buf, max_records=1000, threads=1)
+    par, consumed_p, _ = fastx.index_buffer(buf, max_records=1000, threads=8)
+    assert len(par) == 1000 and consumed_p == consumed_s and par.tobytes() == serial.tobytes()
+    # wrapped (multi-line) FASTQ and FASTA
+    wrapped = "".join("@%s\n%s+\n%s" % (t, "".join(s[j:j + 80] + "\n" for j in range(0, len(s), 80)) or "\n",
+                                          "".join(q[j:j + 80] + "\n" for j in range(0, len(q), 80)) or "\n")
+                      for t, s, q in reads).encode()
+    serial, _, _ = fastx.index_buffer(wrapped, threads=1)
+    par, _, _ = fastx.index_buffer(wrapped, threads=8)
+    assert [int(x) for x in serial["seq_len"]] == [len(s) for _, s, _ in reads] and par.tobytes() == serial.tobytes()
+    fasta = "".join(">%s\n%s" % (t, "".join(s[j:j + 60] + "\n" for j in range(0, len(s), 60)) or "\n") for t, s, _ in reads).encode()
+    serial, _, is_fastq = fastx.index_buffer(fasta, threads=1)
+    par, _, _ = fastx.index_buffer(fasta, threads=8)
+    assert not is_fastq and len(par) == len(reads) and par.tobytes() == serial.tobytes()
+    # errors surface identically
+    broken = buf[:len(buf) // 2] + b"@bad\nACGT\n+\nII\n" + buf[len(buf) // 2:]
+    with pytest.raises(fastx.FastxError):
+        fastx.index_buffer(broken, threads=1)
+    with pytest.raises(fastx.FastxError):
+        fastx.index_buffer(broken, threads=8)
+
+
+@pytest.mark.parametrize("chunk_bytes,multiple_of", [(1 << 20, 1), (1 << 20, 128), (300000, 1000), (64 << 20, 4000)])
+def test_native_reader_chunks(tmp_path, chunk_bytes, multiple_of):
+    reads = _big_reads(4100, 4, "I5#@")
+    path = tmp_path / "r.fastq"
+    path.write_bytes(_fastq_bytes(reads)[:-1])                        # last record without a line break
+    seen = []
+    sizes = []
+    with fastx.Reader(str(path), chunk_bytes, threads=4) as reader:
+        for chunk in reader.chunks(multiple_of):
+            data = chunk.data.tobytes()
+            assert chunk.fastq
+            for r in chunk.recs:
+                seen.append((data[r["title_off"]:r["title_off"] + r["title_len"]].decode(),
+                             data[r["seq_off"]:r["seq_off"] + r["seq_span"]].decode(),
+                             data[r["qual_off"]:r["qual_off"] + r["qual_span"]].decode()))
+            sizes.append(len(chunk))
+            chunk.release()
+    assert seen == reads
+    assert all(s % multiple_of == 0 for s in sizes[:-1]) and sum(sizes) == len(reads)
+
+
+def test_native_reader_errors(tmp_path):
+    bad = tmp_path / "bad.fastq"
+    bad.write_bytes(b"ACGT\n")
+    with fastx.Reader(str(bad)) as reader, pytest.raises(fastx.FastxError, match="must start with"):
+        reader.next_chunk()
+    bad.write_bytes(b"@a\nACGT\n+\nIIII\n@b\nAC\n+\nIIII\n")
+    with fastx.Reader(str(bad)) as reader, pytest.raises(fastx.FastxError, match="quality"):
+        reader.next_chunk()
+    bad.write_bytes(b"@a\nACGT\n+\nIIII\nxyz\n")
+    with fastx.Reader(str(bad)) as reader, pytest.raises(fastx.FastxError):
+        reader.next_chunk()
+    empty = tmp_path / "empty.fastq"
+    empty.write_bytes(b"")
+    with fastx.Reader(str(empty)) as reader:
+        assert reader.next_chunk() is None
+    with pytest.raises(IOError):
+        fastx.Reader(str(tmp_path / "missing.fastq"))
+
+
+def _py_trim(seq, qual, res, trim):
+    if trim:
+        return seq[res["trim5p"]:res["trim3p"]], qual[res["trim5p"]:res["trim3p"]]
+    return seq, qual
+
+
+def test_stream_and_tsv_writers_match_cli_layout():
+    """qcb_format_stream == cli.py:write_to_file without -b (comment + ' barcode=<id>'), qcb_format_tsv ==
+    cli.py:write_multiplexing_result, including repr() of the score, trimming and the min-length filter."""
+    import ctypes
+    from qcat_b200 import _ffi
+    reads = _random_reads(400, 8)
+    buf = _fastq_bytes(reads)
+    recs, _, _ = fastx.index_buffer(buf)
+    n = len(recs)
+    rng = np.random.default_rng(2)
+    results = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+    lens = np.array([len(s) for _, s, _ in reads])
+    results["trim5p"] = rng.integers(0, 80, size=n)
+    results["trim3p"] = np.maximum(lens - rng.integers(0, 80, size=n), 0)
+    results["adapter_end"] = rng.integers(0, 150, size=n)
+    scores = [100.0, 0.0, 97.61904761904762, 58.0, 84.78260869565217, 2.380952380952381, 83.33333333333333, -2.1739130434782608,
+              61.904761904761905, 1e-3, 123456.789]
+    results["barcode_score"] = [scores[i % len(scores)] * (1.0 if i % 3 else 100.0 / 42 / 2.380952380952381) for i in range(n)]
+    strings = ["none", "7", "12", "6/95", "PBC096", "NBD103/NBD104"]
+    blob = np.frombuffer("".join(strings).encode() + b"\0", dtype=np.uint8)
+    off = np.zeros(len(strings) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(s) for s in strings])
+    id_label = rng.integers(0, 4, size=n).astype(np.int32)
+    kit_label = rng.integers(4, 6, size=n).astype(np.int32)
+    lib = _ffi.load()
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+    for trim, min_len in ((0, 0), (1, 0), (1, 100)):
+        kept = np.zeros(n, dtype=np.uint8)
+        need = ctypes.c_int64(0)
+        args = (vp(arr), vp(recs), vp(results), vp(id_label), n, vp(blob), vp(off), len(strings), 1, trim, min_len)
+        assert lib.qcb_format_stream(*args, None, 0, ctypes.byref(need), vp(kept), 4) == 0
+        out = np.zeros(need.value + 1, dtype=np.uint8)
+        assert lib.qcb_format_stream(*args, vp(out), int(out.size), ctypes.byref(need), vp(kept), 4) == 0
+        want, want_tsv = io.StringIO(), io.StringIO()
+        for i, (title, seq, qual) in enumerate(reads):
+            seq, qual = _py_trim(seq, qual, results[i], trim)
+            if len(seq) < min_len:
+                assert not kept[i]
+                continue
+            cols = title.replace("\t", " ").split(" ")
+            name, comment = cols[0], (" ".join(cols[1:]) if len(cols) > 1 else None)
+            bc = strings[id_label[i]]
+            print("@" + name + " " + "{} barcode={}".format(comment or "", bc), seq, "+", qual or "", sep="\n", file=want)
+            if id_label[i]:
+                print(name, len(seq), bc, float(results["barcode_score"][i]), strings[kit_label[i]],
+                      int(results["adapter_end"][i]), comment, sep="\t", file=want_tsv)
+            else:
+                print(name, len(seq), "none", "-1", "none", "-1", comment, sep="\t", file=want_tsv)
+        assert out[:need.value].tobytes().decode() == want.getvalue()
+        tsv_label = np.where(id_label > 0, id_label, -1).astype(np.int32)
+        cap = 200 * n
+        out = np.zeros(cap, dtype=np.uint8)
+        assert lib.qcb_format_tsv(vp(arr), vp(recs), vp(results), vp(tsv_label), vp(kit_label), n, vp(blob), vp(off), len(strings),
+                                  trim, min_len, vp(out), cap, ctypes.byref(need), vp(kept), 4) == 0
+        assert out[:need.value].tobytes().decode() == want_tsv.getvalue()

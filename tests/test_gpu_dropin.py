@@ -139,3 +139,36 @@ def test_native_demux_file_matches_reference_cli(tmp_path, kit, trim):
     assert tsv.getvalue() == tsv_cpu
     assert files_gpu == files_cpu
     assert summary["reads"] == len(reads) and sum(summary["barcodes"].values()) == len(reads) - summary["skipped"]
+
+
+@pytest.mark.parametrize("kit,trim,filter_barcodes", [("NBD103/NBD104", True, False), (None, False, True), ("PBC096", True, True)])
+def test_native_demux_stream_output_matches_reference_cli(tmp_path, kit, trim, filter_barcodes):
+    """Without -b the CLI writes every read to one stream with ' barcode=<id>' comments (cli.py:337-352); demux_file's
+    `output` must be byte-identical, also with --filter-barcodes (per-batch filter, trims reset on filtered reads) and
+    through the parallel record index (chunks > 1 MiB)."""
+    refloader.load()
+    from qcat import scanner as ref_scanner
+    from qcat_b200 import dropin, fastx
+    dropin.uninstall()
+    layouts = ref_scanner.factory(kit=kit or "RBK004").layouts
+    reads = _reads(layouts, 4600, seed=23)
+    fastq = tmp_path / "reads.fastq"
+    with open(fastq, "w") as fh:
+        for i, r in enumerate(reads):
+            fh.write("@read%d%s\n%s\n+\n%s\n" % (i, " ch=%d" % (i % 512) if i % 5 else "", r, "@" * len(r)))
+    argv = ["-f", str(fastq), "--min-read-length", "150"] + (["-k", kit] if kit else []) + (["--trim"] if trim else [])
+    argv += ["--filter-barcodes"] if filter_barcodes else []
+    stream_cpu = _run_cli(argv)
+    tsv_cpu = _run_cli(argv + ["--tsv"])
+
+    dropin.install(device=0)
+    try:
+        sc = ref_scanner.factory(kit=kit, enable_filter_barcodes=filter_barcodes)
+        stream, tsv = io.BytesIO(), io.StringIO()
+        summary = fastx.demux_file(str(fastq), sc, trim=trim, min_read_length=150, output=stream, chunk_bytes=2 << 20)
+        fastx.demux_file(str(fastq), sc, trim=trim, min_read_length=150, tsv=tsv, chunk_bytes=3 << 20)
+    finally:
+        dropin.uninstall()
+    assert stream.getvalue().decode() == stream_cpu
+    assert tsv.getvalue() == tsv_cpu
+    assert summary["reads"] == len(reads)

@@ -2,8 +2,9 @@
 
   python tools/bench_ingest.py [n_reads] [mean_len]
 
-Writes a synthetic FASTQ to /tmp, then times (a) indexing + window packing alone, (b) demux_file without outputs,
-(c) demux_file with trimmed per-barcode FASTQ output.  File I/O goes through the page cache."""
+Writes a synthetic FASTQ to /tmp, then times (a) reading + indexing + window packing alone (1 thread / all cores),
+(b) demux_file without outputs, (c) with the TSV table, (d) with trimmed per-barcode FASTQ output, (e) kit auto.
+File I/O goes through the page cache."""
 import io
 import json
 import os
@@ -33,27 +34,41 @@ def main():
     size = os.path.getsize(path)
     out = {"reads": n, "file_gb": size / 1e9, "cores": os.cpu_count()}
 
-    t0 = time.perf_counter()
-    total = 0
-    for buf, recs, fastq in fastx.iter_chunks(path):
-        fastx.pack_windows(buf, recs, 150)
-        total += len(recs)
-    dt = time.perf_counter() - t0
-    assert total == n
-    out["index_pack"] = {"reads_per_s": n / dt, "gb_per_s": size / 1e9 / dt}
+    threads = os.cpu_count()
+    for label, thr in (("index_pack_1thread", 1), ("index_pack", threads)):
+        best = 1e9
+        for _ in range(2):
+            t0 = time.perf_counter()
+            total = 0
+            with fastx.Reader(path, 64 << 20, thr) as reader:
+                for chunk in reader.chunks(1):
+                    fastx.pack_windows(chunk.data, chunk.recs, 150, thr)
+                    total += len(chunk)
+                    chunk.release()
+            best = min(best, time.perf_counter() - t0)
+        assert total == n
+        out[label] = {"reads_per_s": n / best, "gb_per_s": size / 1e9 / best, "threads": thr}
 
-    fastx.demux_file(path, sc)                                   # warm-up (plan, workspace)
-    t0 = time.perf_counter()
-    summary = fastx.demux_file(path, sc)
-    dt = time.perf_counter() - t0
-    out["demux_no_output"] = {"reads_per_s": n / dt, "gb_per_s": size / 1e9 / dt,
-                              "classified": 1.0 - summary["barcodes"].get("none", 0) / n}
+    def timed(**kw):
+        fastx.demux_file(path, sc, keep_records=False, **kw)        # warm-up (plan, workspace, page cache)
+        t0 = time.perf_counter()
+        summary = fastx.demux_file(path, sc, keep_records=False, **kw)
+        dt = time.perf_counter() - t0
+        return summary, {"reads_per_s": n / dt, "gb_per_s": size / 1e9 / dt}
 
+    summary, out["demux_no_output"] = timed()
+    out["demux_no_output"]["classified"] = 1.0 - summary["barcodes"].get("none", 0) / n
+    with open(os.devnull, "wb") as sink:
+        _, out["demux_tsv"] = timed(tsv=sink)
     outdir = tempfile.mkdtemp(prefix="qcb_out_")
+    _, out["demux_trim_write"] = timed(trim=True, out_dir=outdir)
+    auto = scanner.BarcodeScannerEPI2ME(device=0)                   # kit auto: per-batch vote over 12 layouts
     t0 = time.perf_counter()
-    fastx.demux_file(path, sc, trim=True, out_dir=outdir)
+    fastx.demux_file(path, auto, keep_records=False)
+    t0 = time.perf_counter()
+    fastx.demux_file(path, auto, keep_records=False)
     dt = time.perf_counter() - t0
-    out["demux_trim_write"] = {"reads_per_s": n / dt, "gb_per_s": size / 1e9 / dt}
+    out["demux_auto_kit"] = {"reads_per_s": n / dt, "gb_per_s": size / 1e9 / dt}
     print(json.dumps(out))
     os.remove(path)
 
