@@ -1,11 +1,20 @@
 // Barcode stage, packed kernels (included from kernels_fast.cuh; structs FastDev / FastGroup live there).
 //
 //   k_context       per (window, set) task: the two shared-context columns F and G and the base codes of the region,
-//                   packed one u32 per DP row:  code (4 bits) | F (14 bits) | G (14 bits), W space.
+//                   packed one u32 per DP row (W space):  profile-row offset of the base code (bits 4..9) |
+//                   F (11 bits, from bit 10) | G (11 bits, from bit 21).
 //   k_barcode_fast  lane = window x two barcodes, profile from shared memory (any set size).
 // (textually included inside namespace qcb by kernels_fast.cuh)
 
 constexpr int kRowTile = 32;                       // tasks per row-info tile
+
+// Row-info word.  The base code is stored as the byte offset of its profile row inside a pair's profile block:
+// code * kProfRowBytes = code * 144 = (code << 4) | (code << 7) for code < 8, so `block address | (info & kRowCodeMask)`
+// is the row's shared-memory address (blocks are 1 KB aligned) -- one LOP3 instead of a multiply-add chain.
+constexpr uint32_t kRowCodeMask = 0x3f0u;
+constexpr int kRowFShift = 10, kRowGShift = 21;
+constexpr uint32_t kRowFMask = 0x7ffu;
+__device__ __forceinline__ uint32_t rowinfo_code(int code) { return ((uint32_t)code << 4) | ((uint32_t)code << 7); }
 
 __device__ __forceinline__ long long rowinfo_base(long long task)
 {
@@ -83,8 +92,8 @@ k_context(FastDev f, DevTables t, const uint32_t *__restrict__ ctx_tab, const ui
         // the later one ORs into it (same thread, so program order makes the read see the earlier store).
         uint32_t *out = rowinfo + tile * (long long)(kRows * kRowTile) + lane;
         if (n > 0) {
-            out[0] = (uint32_t)(u * g) << 4;                                  // F[0]
-            out[(long long)n * kRowTile] = (uint32_t)(d * g) << 18;            // G[n]: row 0 of the reversed problem
+            out[0] = (uint32_t)(u * g) << kRowFShift;                          // F[0]
+            out[(long long)n * kRowTile] = (uint32_t)(d * g) << kRowGShift;    // G[n]: row 0 of the reversed problem
         }
         const uint32_t gdup = dup16((uint32_t)g);
         uint32_t border = 0;
@@ -112,7 +121,7 @@ k_context(FastDev f, DevTables t, const uint32_t *__restrict__ ctx_tab, const ui
                 Wc[c] = left;
             }
             if (st <= n) {
-                const uint32_t fword = (uint32_t)cf | ((left & 0xffffu) << 4), gword = (left >> 16) << 18;
+                const uint32_t fword = rowinfo_code(cf) | ((left & 0xffffu) << kRowFShift), gword = (left >> 16) << kRowGShift;
                 uint32_t *pf_out = out + (long long)st * kRowTile, *pg_out = out + (long long)(n - st) * kRowTile;
                 if (2 * st < n) { *pf_out = fword; *pg_out = gword; }
                 else if (2 * st == n) { *pf_out = fword | gword; }
@@ -149,14 +158,35 @@ __device__ __forceinline__ void store_pair_scores(const uint32_t (&Wc)[kCore], u
     if (2 * pr + 1 < G.nb) dst[2 * pr + 1] = s1;
 }
 
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 // Lane = window x two barcodes (u16 halves); warp = 32 windows x one barcode pair; profile rows via multicast LDS.
+// The kernel runs at the issue limit of its instruction mix (add + VIMNMX3 per cell pair, ~2.7 warp-instructions per
+// clock per SM), so the row loop is written to need as few instructions as possible around the 48 essential ones:
+// one LOP3 for the profile address (see kRowCodeMask), a pointer-compare loop, diagonal terms issued one column ahead
+// of the in-place max chain so that no register copies are needed.
 __global__ void __launch_bounds__(kBarcodeWarps * 32, 3)
 k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots,
                const uint32_t *__restrict__ rowinfo, const int4 *__restrict__ taskmeta, int32_t *__restrict__ bc_score)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint32_t *s_prof = (uint32_t *)smem;
-    uint32_t *s_row = (uint32_t *)(smem + f.profile_bytes);          // [kRows][32]: code | F << 4 | G << 18
+    extern __shared__ __align__(1024) uint8_t smem_bc[];
+    uint8_t *smem = smem_bc;
+    uint32_t *s_prof = (uint32_t *)smem;                             // [pair][code][kProfRowBytes], 1 KB per pair
+    uint32_t *s_row = (uint32_t *)(smem + f.profile_bytes);          // [kRows][32] row-info words
+    const uint32_t prof_addr = (uint32_t)__cvta_generic_to_shared(s_prof);
+    const uint32_t row_addr = (uint32_t)__cvta_generic_to_shared(s_row);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -190,42 +220,46 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots,
         int32_t *dst = bc_score + w * bslots + (k ? bmax0 : 0);
         for (int pr = warp; pr < npairs_max; pr += (int)(blockDim.x >> 5)) {
             const int pcl = min(pr, npairs - 1);
-            const uint8_t *prow = (const uint8_t *)s_prof + G.prof_off + pcl * (f.n_codes * kProfWords * 4);
+            const uint32_t block = prof_addr + (uint32_t)G.prof_off + (uint32_t)pcl * kProfPairBytes;
             uint32_t Wc[kCore];
 #pragma unroll
             for (int c = 0; c < kCore; ++c) Wc[c] = dup16((uint32_t)((G.u + max(0, c + 1 - G.pad)) * g));
             const uint32_t info0 = s_row[lane];
-            uint32_t Fprev = dup16((info0 >> 4) & 0x3fffu);
-            uint32_t acc = dup16((uint32_t)(v * g)) + dup16(info0 >> 18);          // join term of row 0
+            uint32_t Fprev = dup16((info0 >> kRowFShift) & kRowFMask);
+            uint32_t acc = dup16((uint32_t)(v * g)) + dup16(info0 >> kRowGShift);  // join term of row 0
             int i = 1;
             while (i <= nmax) {
                 // rows up to the next row at which some lane's region ends run without per-lane branching; a lane's
                 // scores are taken at its own last row, so whatever it computes afterwards is never used
                 const int ev = __reduce_min_sync(0xffffffffu, n >= i ? n : INT32_MAX);
-                for (; i <= ev; ++i) {
-                    const uint32_t info = s_row[i * kRowTile + lane];
-                    const uint4 *prow_i = (const uint4 *)(prow + (info & 15u) * (kProfWords * 4));
+                uint32_t rp = row_addr + (uint32_t)(i * kRowTile + lane) * 4u;
+                const uint32_t rp_end = row_addr + (uint32_t)((ev + 1) * kRowTile + lane) * 4u;
+                i = ev + 1;
+#pragma unroll 1
+                do {
+                    const uint32_t info = lds32(rp);
+                    rp += kRowTile * 4;
+                    const uint32_t prow = block | (info & kRowCodeMask);
+                    const uint32_t Fi = dup16((info >> kRowFShift) & kRowFMask);
+                    const uint32_t Gi = dup16(info >> kRowGShift);
                     uint32_t e[kCore];
 #pragma unroll
                     for (int c = 0; c < kCore; c += 4) {
-                        const uint4 q = prow_i[c >> 2];
+                        const uint4 q = lds128(prow + c * 4);
                         e[c] = q.x; e[c + 1] = q.y; e[c + 2] = q.z; e[c + 3] = q.w;
                     }
-                    const uint32_t Fi = dup16((info >> 4) & 0x3fffu);
-                    const uint32_t Gi = dup16(info >> 18);
-                    // diagonal terms first (previous row's registers), then the in-place left-to-right max chain
-                    e[0] += Fprev;
-#pragma unroll
-                    for (int c = 1; c < kCore; ++c) e[c] += Wc[c - 1];
                     uint32_t left = Fi;
+                    uint32_t t = e[0] + Fprev;
 #pragma unroll
                     for (int c = 0; c < kCore; ++c) {
-                        left = __vimax3_u16x2(e[c], Wc[c], left);
+                        const uint32_t tn = c + 1 < kCore ? e[c + 1] + Wc[c] : 0u;   // next column's diagonal term first
+                        left = __vimax3_u16x2(t, Wc[c], left);
                         Wc[c] = left;
+                        t = tn;
                     }
                     Fprev = Fi;
                     acc = __viaddmax_u16x2(left, Gi, acc);
-                }
+                } while (rp != rp_end);
                 if (n == ev && pr < npairs) store_pair_scores(Wc, acc, G, n, g, rup, pr, dst);
             }
         }

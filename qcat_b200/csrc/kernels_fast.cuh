@@ -15,6 +15,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -24,7 +25,8 @@
 namespace qcb {
 
 constexpr int kCore = 24;                 // core (barcode-specific) columns held in registers
-constexpr int kProfWords = 28;            // words per (pair, code) profile row: 24 used + 4 pad (bank spread)
+constexpr int kProfWords = 36;            // words per (pair, code) profile row: 24 used + 12 pad; 144 B = (1 << 4) | (1 << 7)
+constexpr int kProfPairBytes = 1024;      // one pair's profile block (<= 7 codes x 144 B), 1 KB aligned: see kRowCodeMask
 constexpr int kRows = kFastMaxStride + 1; // DP rows 0..160
 constexpr int kTile = 32;                 // windows per tile (one per lane)
 constexpr int kBarcodeWarps = 8;
@@ -41,7 +43,7 @@ struct FastGroup {          // one template group (layout, set k)
 };
 
 struct FastDev {
-    const uint32_t *profile;     // [set][pair][code][kProfWords]
+    const uint32_t *profile;     // [set][pair] blocks of kProfPairBytes: [code][kProfWords]
     int32_t profile_bytes;
     const FastGroup *groups;     // [n_groups]
     int32_t n_codes;             // bmat_size
@@ -71,7 +73,7 @@ struct FastPlan {
     const uint32_t *ctx_tab = nullptr;   // device: k_context score tables
     int ctx_ncol = 12;
     size_t context_smem = 0;
-    void *rowinfo = nullptr;         // [tiles][kRows][32] u32: code | F << 4 | G << 18
+    void *rowinfo = nullptr;         // [tiles][kRows][32] u32: code row offset | F << 10 | G << 21 (kernels_barcode_fast.cuh)
     void *taskmeta = nullptr;        // [tasks] int4 {region length, group, R over prefix columns, -}
     size_t rowinfo_bytes = 0, taskmeta_bytes = 0;
     // adapter stage: host copies used to build per-subset profiles
@@ -289,6 +291,7 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     const int nc = h->bmat_size;
     // --- scoring preconditions: linear gap, non-negative shifted scores, values fit 15 bits ---
     if (h->barcode_open != h->barcode_extend || g <= 0) return 0;
+    if (nc * kProfWords * 4 > kProfPairBytes || nc > 8) return 0;     // a pair's profile block holds <= 7 code rows
     int smax = 0;
     for (int i = 0; i < nc * nc; ++i) {
         if (h->bmat[i] + 2 * g < 0) return 0;
@@ -327,7 +330,7 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
         int core = tlen - u - d;
         while (core > kCore && u < kMaxCtx && nb == 1) { ++u; --core; }
         if (core < 1 || core > kCore) return 0;
-        if (smax * tlen + (kFastMaxStride + tlen) * g + 64 >= 16384) return 0;      // F / G are packed into 14 bits
+        if (smax * tlen + (kFastMaxStride + tlen) * g + 64 >= 2048) return 0;       // F / G are packed into 11 bits
         G.u = u; G.d = d; G.pad = kCore - core; G.tlen = tlen; G.nb = nb;
         fp.max_pairs = std::max(fp.max_pairs, (nb + 1) / 2);
         G.up_off = (int32_t)ctx.size();
@@ -349,19 +352,18 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
             set_keys.push_back(key);
             set_off.push_back((int)(profile.size() * 4));
             const int npairs = (nb + 1) / 2;
-            for (int pr = 0; pr < npairs; ++pr)
+            for (int pr = 0; pr < npairs; ++pr) {
+                const size_t base = profile.size();
+                profile.resize(base + kProfPairBytes / 4, 0u);
                 for (int code = 0; code < nc; ++code)
-                    for (int c = 0; c < kProfWords; ++c) {
-                        uint32_t word = 0;
-                        if (c >= G.pad && c < kCore) {
-                            int ba = 2 * pr, bb = std::min(2 * pr + 1, nb - 1);
-                            int ca = key[1 + ba * core + (c - G.pad)], cb = key[1 + bb * core + (c - G.pad)];
-                            uint32_t lo = (uint32_t)(h->bmat[code * nc + ca] + 2 * g);
-                            uint32_t hi = (uint32_t)(h->bmat[code * nc + cb] + 2 * g);
-                            word = lo | (hi << 16);
-                        }
-                        profile.push_back(word);
+                    for (int c = G.pad; c < kCore; ++c) {
+                        int ba = 2 * pr, bb = std::min(2 * pr + 1, nb - 1);
+                        int ca = key[1 + ba * core + (c - G.pad)], cb = key[1 + bb * core + (c - G.pad)];
+                        uint32_t lo = (uint32_t)(h->bmat[code * nc + ca] + 2 * g);
+                        uint32_t hi = (uint32_t)(h->bmat[code * nc + cb] + 2 * g);
+                        profile[base + (size_t)code * kProfWords + c] = lo | (hi << 16);
                     }
+            }
         }
         G.prof_off = set_off[found];
     }

@@ -135,13 +135,50 @@ class GpuScannerMixin(object):
         return plan.detect(win5, tail3, wlen, read_len, self._subset_for(plan, kits))
 
     def _apply_middle_scan(self, read_sequences, results, qcat_config):
-        """--detect-middle (scanner_base.py:479-519, :593-595): reads whose body still holds an adapter -> 997."""
-        for i, (seq, result) in enumerate(zip(read_sequences, results)):
-            if result["adapter"] and self.scan_middle(seq, result["adapter"].kit, qcat_config):
-                trims = result["trim5p"], result["trim3p"]
-                results[i] = empty_return_dict()
-                results[i]["exit_status"] = 997
-                results[i]["trim5p"], results[i]["trim3p"] = trims
+        """--detect-middle (scanner_base.py:479-519, :593-595): reads whose body still holds an adapter -> 997.
+
+        The reference scans read[W:-W] and, if that scores < 50, its reverse complement, one read at a time; only the
+        boolean is used, so here both windows of every read that has an adapter go to the device together, grouped by
+        detected kit and by length (window buffers of one call are bounded to ~256 MB)."""
+        W = qcat_config.max_align_length
+        by_kit = {}
+        for i, result in enumerate(results):
+            if result["adapter"]:
+                by_kit.setdefault(result["adapter"].kit, []).append(i)
+        for kit_name, indices in by_kit.items():
+            detected = self.get_adapters(kit_name)
+            if not detected:
+                raise IndexError("list index out of range")      # bc_adapter_templates[-1] in the reference's scan()
+            try:
+                plan = self._plan_for(qcat_config)
+                subset = self._subset_for(plan, detected)
+            except KeyError:
+                plan = self._plan_for(qcat_config, layouts=detected)
+                subset = list(range(len(detected)))
+            indices.sort(key=lambda i: len(read_sequences[i] or ""))
+            start = 0
+            while start < len(indices):
+                stop, longest = start, 16
+                while stop < len(indices):
+                    longest_next = max(longest, len(read_sequences[indices[stop]] or ""))
+                    if stop > start and 2 * (stop + 1 - start) * longest_next > (256 << 20):
+                        break
+                    longest = longest_next
+                    stop += 1
+                windows = []
+                for i in indices[start:stop]:
+                    body = (read_sequences[i] or "")[W:-W]
+                    windows.append(body)
+                    windows.append(revcomp(body))
+                recs = plan.scan_windows(windows, subset)
+                found = ~(recs["barcode_score"] < 50.0)
+                for j, i in enumerate(indices[start:stop]):
+                    if found[2 * j] or found[2 * j + 1]:
+                        trims = results[i]["trim5p"], results[i]["trim3p"]
+                        results[i] = empty_return_dict()
+                        results[i]["exit_status"] = 997
+                        results[i]["trim5p"], results[i]["trim3p"] = trims
+                start = stop
 
     def scan_middle(self, sequence, kit_name, qcat_config):
         detected = self.get_adapters(kit_name)

@@ -172,3 +172,38 @@ def test_native_demux_stream_output_matches_reference_cli(tmp_path, kit, trim, f
     assert stream.getvalue().decode() == stream_cpu
     assert tsv.getvalue() == tsv_cpu
     assert summary["reads"] == len(reads)
+
+
+@pytest.mark.parametrize("mode,kit", [("epi2me", "PBC096"), ("epi2me", None), ("dual", None)])
+def test_middle_adapter_scan_matches_reference(mode, kit):
+    """--detect-middle (scanner_base.py:479-519, :593-595): chimeric reads (two reads joined, so adapters sit in the
+    body) get exit_status 997 exactly where the reference's CPU path says so, single-read and batch API; the drop-in
+    scores all bodies of a batch in one device call."""
+    refloader.load()
+    from qcat import config as ref_config
+    from qcat import scanner as ref_scanner
+    from qcat_b200 import dropin
+    dropin.uninstall()
+    cfg = ref_config.qcatConfig()
+    cpu = ref_scanner.factory(mode=mode, kit=kit, scan_middle_adapter=True)
+    # low error rates: at the default ones the adapter rarely scores > 90 and the reference then only looks at
+    # body[:150] for the barcode (scanner_epi2me.py:74-82), so hardly any middle adapter is found
+    from qcat_b200 import synth
+    layouts = cpu.layouts if kit or mode == "dual" else ref_scanner.factory(kit="RBK004").layouts
+    plain = synth.windows_to_reads(synth.generate(layouts, 120, seed=31, mean_len=1200.0, sub=0.02, dele=0.01, ins=0.01))
+    reads = []
+    for i in range(0, len(plain), 2):
+        reads.append(plain[i] + plain[i + 1] if i % 3 else plain[i])         # two thirds chimeric
+    reads += ["", "ACGT" * 60, plain[0][:310], plain[1][:299]]
+    want = cpu.detect_barcode_batch(reads, [None] * len(reads), cfg)
+    want_single = [cpu.detect_barcode(r, None, cfg) for r in reads[:12]]
+    assert sum(r["exit_status"] == 997 for r in want) >= 5
+    dropin.install(device=0)
+    try:
+        gpu = ref_scanner.factory(mode=mode, kit=kit, scan_middle_adapter=True)
+        got = gpu.detect_barcode_batch(reads, [None] * len(reads), cfg)
+        got_single = [gpu.detect_barcode(r, None, cfg) for r in reads[:12]]
+    finally:
+        dropin.uninstall()
+    assert [_key(r) for r in got] == [_key(r) for r in want]
+    assert [_key(r) for r in got_single] == [_key(r) for r in want_single]
