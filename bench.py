@@ -323,6 +323,18 @@ def run_ours(args):
         compute["executed_cells_per_read"] = kernel_cells
         compute["executed_achieved"] = kernel_cells * n / (step_ms * 1e-3)
         compute["executed_frac"] = compute["executed_achieved"] / cell_peak
+        if dom == "barcode" and not args.force_generic:
+            # What binds k_barcode_fast (ncu: LSU wavefronts 93 % of peak): every cell pair needs one 32-bit
+            # substitution word gathered from shared memory by the lane's own base code, and the crossbar delivers 4 B
+            # per lane per clock -- one wavefront per warp (32 windows x one barcode pair) per core column, plus one for
+            # the row-info word.  Peak = 1 wavefront / clock / SM at the SM clock sampled under load.
+            wavefronts_per_read = region_rows * (nb / 2.0) * 25.0 / 32.0
+            peak_wf = plan.info()["sm_count"] * load_mhz * 1e6
+            achieved_wf = wavefronts_per_read * n / (dom_ms * 1e-3)
+            compute["smem_gather_roofline"] = {"kernel": "k_barcode_fast", "unit": "shared-memory wavefronts/s",
+                                               "wavefronts_per_read": wavefronts_per_read, "achieved": achieved_wf,
+                                               "peak": peak_wf, "frac": achieved_wf / peak_wf,
+                                               "evidence": "profiles/r01c_barcode_full.md"}
 
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside) ------------
     e2e = None

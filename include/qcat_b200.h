@@ -203,6 +203,11 @@ int qcb_format_tsv(const char *buf, const qcb_fastx_record *recs, const qcb_resu
                    int32_t trim, int64_t min_read_length, uint8_t *out, int64_t out_capacity, int64_t *out_bytes,
                    uint8_t *kept, int32_t threads);
 
+/* Append every non-empty bin of a qcb_format_records buffer to its file descriptor (fds[n_bins], -1 = bin has no
+ * file), `threads` bins at a time -- the `-b` per-barcode files of cli.py:309-336. */
+int qcb_write_bins(const int32_t *fds, const uint8_t *out, const int64_t *bin_offset, const int64_t *bin_bytes, int32_t n_bins,
+                   int32_t threads);
+
 /* Chunked reader replacing iter_fastx (cli.py:235-306) for files: qcb_reader_next() returns the next chunk of complete
  * records (bytes read with `threads` concurrent preads, indexed with qcb_fastx_index_mt); every chunk but the last holds
  * a multiple of `multiple_of` records so that CLI batches of 4000 stay aligned.  *chunk = NULL at the end of the file.

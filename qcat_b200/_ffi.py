@@ -103,7 +103,7 @@ EXPORTS = ("qcb_device_count", "qcb_last_error", "qcb_version", "qcb_plan_create
            "qcb_plan_set_force_generic", "qcb_plan_set_profiling", "qcb_plan_stage_times", "qcb_sg_batch", "qcb_scan", "qcb_detect", "qcb_detect_device", "qcb_kit_vote",
            "qcb_kit_vote_device", "qcb_histogram_device", "qcb_microbench_cell_rate", "qcb_io_last_error", "qcb_fastx_index",
            "qcb_pack_windows", "qcb_format_records", "qcb_fastx_index_mt", "qcb_format_stream", "qcb_format_tsv",
-           "qcb_reader_open", "qcb_reader_next", "qcb_chunk_data", "qcb_chunk_records", "qcb_chunk_release", "qcb_reader_close")
+           "qcb_write_bins", "qcb_reader_open", "qcb_reader_next", "qcb_chunk_data", "qcb_chunk_records", "qcb_chunk_release", "qcb_reader_close")
 
 _lib = None
 
@@ -169,6 +169,8 @@ def load():
     lib.qcb_format_stream.argtypes = [vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, i64, vp, i64, vp, vp, i32]
     lib.qcb_format_tsv.restype = ctypes.c_int
     lib.qcb_format_tsv.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, i64, vp, i64, vp, vp, i32]
+    lib.qcb_write_bins.restype = ctypes.c_int
+    lib.qcb_write_bins.argtypes = [vp, vp, vp, vp, i32, i32]
     lib.qcb_reader_open.restype = vp
     lib.qcb_reader_open.argtypes = [ctypes.c_char_p, i64, i32]
     lib.qcb_reader_next.restype = ctypes.c_int

@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <cerrno>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -605,6 +607,47 @@ int qcb_format_tsv(const char *buf, const qcb_fastx_record *recs, const qcb_resu
     if (total > out_capacity) return io_fail("output buffer too small: need %lld bytes", (long long)total);
     int64_t at = 0;
     for (const std::string &p : part) { memcpy(out + at, p.data(), p.size()); at += (int64_t)p.size(); }
+    return 0;
+}
+
+// Append bin b's bytes (out + bin_offset[b], bin_bytes[b]) to the file descriptor fds[b] for every bin with bytes, using
+// `threads` writers that pick bins from a shared counter (one writer per file, so the order inside a file is kept).
+int qcb_write_bins(const int32_t *fds, const uint8_t *out, const int64_t *bin_offset, const int64_t *bin_bytes, int32_t n_bins,
+                   int32_t threads)
+{
+    if (n_bins <= 0) return 0;
+    if (!fds || !out || !bin_offset || !bin_bytes) return io_fail("NULL argument");
+    std::vector<int32_t> todo;
+    for (int32_t b = 0; b < n_bins; ++b) {
+        if (bin_bytes[b] <= 0) continue;
+        if (fds[b] < 0) return io_fail("no file descriptor for bin %d", (int)b);
+        todo.push_back(b);
+    }
+    std::sort(todo.begin(), todo.end(), [&](int32_t a, int32_t b) { return bin_bytes[a] > bin_bytes[b]; });
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    auto work = [&]() {
+        for (;;) {
+            const size_t k = next.fetch_add(1);
+            if (k >= todo.size()) return;
+            const int32_t b = todo[k];
+            const uint8_t *p = out + bin_offset[b];
+            int64_t left = bin_bytes[b];
+            while (left > 0) {
+                const ssize_t w = write(fds[b], p, (size_t)std::min<int64_t>(left, (int64_t)1 << 30));
+                if (w < 0) { if (errno == EINTR) continue; failed.store(errno ? errno : 1); return; }
+                p += w; left -= w;
+            }
+        }
+    };
+    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, (int)threads), todo.size()));
+    if (T == 1) work();
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t) pool.emplace_back(work);
+        for (auto &th : pool) th.join();
+    }
+    if (failed.load()) return io_fail("write failed: %s", strerror(failed.load()));
     return 0;
 }
 

@@ -281,12 +281,18 @@ class _Writer(object):
         self.kit_counts = {}
         self.total = self.skipped = 0
         self._own_output = None
+        self._buf = np.empty(0, dtype=np.uint8)                  # formatting buffer, reused so its pages stay mapped
         if out_dir:
             os.makedirs(out_dir, exist_ok=True)
         if isinstance(output, (str, bytes, os.PathLike)):
             self._own_output = self.output = open(output, "wb")
         if tsv is not None:
             self._write(tsv, b"name\tlength\tbarcode\tscore\tkit\tadapter_end\tcomment\n")
+
+    def _buffer(self, size):
+        if self._buf.size < size:
+            self._buf = np.empty(int(size) + int(size) // 4 + 4096, dtype=np.uint8)
+        return self._buf
 
     @staticmethod
     def _write(fh, data):
@@ -340,7 +346,7 @@ class _Writer(object):
         if self.tsv is not None:
             tsv_label = np.where(called, id_label, -1).astype(np.int32)
             cap = int(recs["title_len"].sum()) + 160 * n + 64
-            out = np.empty(cap, dtype=np.uint8)
+            out = self._buffer(cap)
             _check_io(lib.qcb_format_tsv(_vp(chunk.data), _vp(recs), _vp(results), _vp(tsv_label), _vp(kit_label), n, _vp(blob),
                                          _vp(off), len(strings), 1 if self.trim else 0, self.min_read_length, _vp(out), cap,
                                          ctypes.byref(need), _vp(kept_u8), self.threads))
@@ -352,25 +358,28 @@ class _Writer(object):
             args = (_vp(chunk.data), _vp(recs), _vp(results), _vp(name_label), n, n_bins, 1 if chunk.fastq else 0,
                     1 if self.trim else 0, self.min_read_length, _vp(bin_bytes))
             _check_io(lib.qcb_format_records(*args, None, 0, _vp(bin_off), _vp(kept_u8), self.threads))
-            out = np.empty(int(bin_bytes.sum()) + 1, dtype=np.uint8)
+            out = self._buffer(int(bin_bytes.sum()) + 1)
             _check_io(lib.qcb_format_records(*args, _vp(out), int(out.size), _vp(bin_off), _vp(kept_u8), self.threads))
+            fds = np.full(n_bins, -1, dtype=np.int32)
             for index in np.nonzero(bin_bytes)[0]:
                 name = strings[index].replace("/", "_")
                 if name not in self.files:
-                    self.files[name] = open(os.path.join(self.out_dir, name + (".fastq" if chunk.fastq else ".fasta")), "wb")
-                self.files[name].write(out[bin_off[index]:bin_off[index] + bin_bytes[index]].data)
+                    self.files[name] = os.open(os.path.join(self.out_dir, name + (".fastq" if chunk.fastq else ".fasta")),
+                                               os.O_WRONLY | os.O_CREAT | os.O_TRUNC | os.O_APPEND, 0o666)
+                fds[index] = self.files[name]
+            _check_io(lib.qcb_write_bins(_vp(fds), _vp(out), _vp(bin_off), _vp(bin_bytes), n_bins, self.threads))
         elif self.output is not None:
             # cli.py:552: the single stream is written when there is no -b folder
             args = (_vp(chunk.data), _vp(recs), _vp(results), _vp(id_label), n, _vp(blob), _vp(off), len(strings),
                     1 if chunk.fastq else 0, 1 if self.trim else 0, self.min_read_length)
             _check_io(lib.qcb_format_stream(*args, None, 0, ctypes.byref(need), _vp(kept_u8), self.threads))
-            out = np.empty(need.value + 1, dtype=np.uint8)
+            out = self._buffer(need.value + 1)
             _check_io(lib.qcb_format_stream(*args, _vp(out), int(out.size), ctypes.byref(need), _vp(kept_u8), self.threads))
             self._write(self.output, out[:need.value].data)
 
     def close(self):
-        for fh in self.files.values():
-            fh.close()
+        for fd in self.files.values():
+            os.close(fd)
         if self._own_output is not None:
             self._own_output.close()
 
