@@ -101,6 +101,34 @@ class GpuScannerMixin(object):
         result["trim3p"] = int(rec["trim3p"])
         return result
 
+    def _records_to_dicts(self, plan, recs):
+        """_record_to_dict for a whole batch: columns are converted to Python objects once (a structured-array row
+        access costs ~10 us, this loop ~0.5 us per read)."""
+        tables = plan.tables
+        layouts = tables.layouts
+        dual = tables.mode == 1
+        barcodes = {}
+        out = []
+        for layout_index, barcode_index, score, adapter_end, trim5p, trim3p, exit_status in zip(
+                recs["layout"].tolist(), recs["barcode"].tolist(), recs["barcode_score"].tolist(), recs["adapter_end"].tolist(),
+                recs["trim5p"].tolist(), recs["trim3p"].tolist(), recs["exit_status"].tolist()):
+            if layout_index < 0:
+                out.append({"barcode": None, "barcode_score": 0.0, "adapter": None, "adapter_end": 0,
+                            "trim5p": trim5p, "trim3p": trim3p, "exit_status": exit_status})
+                continue
+            key = (layout_index, barcode_index)
+            barcode = barcodes.get(key)
+            if barcode is None:
+                barcode = tables.barcode_object(layout_index, barcode_index)
+                if dual:                          # synthesised pair (scanner_dual.py:132-136)
+                    first, second = barcode
+                    barcode = Barcode("barcode{:02d}/{:02d}".format(first.id, second.id),
+                                      "{}/{}".format(first.id, second.id), None, True)
+                barcodes[key] = barcode
+            out.append({"barcode": barcode, "barcode_score": score, "adapter": layouts[layout_index],
+                        "adapter_end": adapter_end, "trim5p": trim5p, "trim3p": trim3p, "exit_status": exit_status})
+        return out
+
     # ---- reference API ---------------------------------------------------------------------------
 
     def scan(self, read_sequence, read_qualities, bc_adapter_templates, nobc_adapter_templates,
@@ -255,7 +283,7 @@ class GpuScannerMixin(object):
                 records = self._detect_records(plan, packed, self._kits())
             finally:
                 self.override_kit_name = None
-            results = [self._record_to_dict(plan, rec) for rec in records]
+            results = self._records_to_dicts(plan, records)
             if self.scan_middle_adapter:
                 self.override_kit_name = kit_name
                 try:

@@ -155,3 +155,34 @@ def test_oracle_counts_reference_cells():
     wlen = np.full(50, 150, dtype=np.int32)
     cells, full = helpers.oracle_count_cells(tables, win, win, wlen)
     assert full == 100 and cells == 50 * (35700 + 1209600)
+
+
+@pytest.mark.parametrize("mode", ["epi2me", "dual"])
+def test_batch_record_conversion_equals_per_record(mode):
+    """GpuScannerMixin._records_to_dicts (columns converted once) builds the same dicts, with the same Barcode /
+    AdapterLayout objects, as _record_to_dict row by row."""
+    from qcat_b200 import _ffi, config, scanner
+    from qcat_b200.tables import Tables
+    sc = scanner.BarcodeScannerEPI2ME(kit="PBC096") if mode == "epi2me" else scanner.BarcodeScannerDual()
+    tables = Tables(sc.layouts, config.qcatConfig(), mode, sc.min_quality)
+
+    class FakePlan(object):
+        pass
+    plan = FakePlan()
+    plan.tables = tables
+    rng = np.random.default_rng(3)
+    recs = np.zeros(500, dtype=_ffi.RESULT_DTYPE)
+    recs["layout"] = rng.integers(-1, len(sc.layouts), 500)
+    recs["barcode"] = rng.integers(0, 96, 500)
+    recs["barcode_score"] = rng.random(500) * 100
+    recs["adapter_end"] = rng.integers(0, 150, 500)
+    recs["trim5p"] = rng.integers(0, 150, 500)
+    recs["trim3p"] = rng.integers(150, 9000, 500)
+    recs["exit_status"] = np.where(recs["layout"] < 0, rng.choice([1, 1002], 500), 0)
+    one_by_one = [sc._record_to_dict(plan, r) for r in recs]
+    batch = sc._records_to_dicts(plan, recs)
+    assert batch == one_by_one
+    for a, b in zip(batch, one_by_one):
+        assert a["adapter"] is b["adapter"] and type(a["barcode_score"]) is float and type(a["trim5p"]) is int
+        if mode == "epi2me":
+            assert a["barcode"] is b["barcode"]
