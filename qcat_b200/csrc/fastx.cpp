@@ -848,6 +848,7 @@ int qcb_reader_next(qcb_reader *rd, int64_t multiple_of, qcb_chunk **chunk)
             rd->carry_len = total - cut;
             if (rd->carry_len > 64 * rd->chunk_bytes) { qcb_chunk_release(c); rd->carry_len = 0; return io_fail("record larger than 64 chunks"); }
             if (keep == 0) {                                          // nothing to hand out yet: keep reading into this buffer
+                if (cut > 0) memmove(c->data, c->data + cut, (size_t)rd->carry_len);
                 rd->pending = c;
                 continue;
             }

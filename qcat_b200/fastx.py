@@ -418,20 +418,22 @@ def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min
         chunk_bytes = (256 << 20) if batched else (64 << 20)
 
     def produce():
+        reader = None
         try:
-            with Reader(path, chunk_bytes, threads) as reader:
-                for chunk in reader.chunks(multiple_of):
-                    if failure:
-                        chunk.release()
-                        break
-                    packed = pack_windows(chunk.data, chunk.recs, qcat_config.max_align_length, threads)
-                    packed_q.put((chunk, packed))
-                    # the reader outlives its chunks: wait for the consumer before closing it
-                packed_q.put(_STOP)
-                done.wait()
+            reader = Reader(path, chunk_bytes, threads)
+            for chunk in reader.chunks(multiple_of):
+                if failure:
+                    chunk.release()
+                    break
+                packed = pack_windows(chunk.data, chunk.recs, qcat_config.max_align_length, threads)
+                packed_q.put((chunk, packed))
         except BaseException as exc:                           # noqa: BLE001 -- re-raised on the caller's thread
             failure.append(exc)
+        finally:
             packed_q.put(_STOP)
+            done.wait()                                        # the reader owns the chunks: it must outlive all of them
+            if reader is not None:
+                reader.close()
 
     def consume():
         try:

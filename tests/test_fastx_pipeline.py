@@ -1,0 +1,122 @@
+"""CPU: qcat_b200.fastx.demux_file (native reader -> window packing -> batch logic -> native writers, three pipeline
+threads) against the UNMODIFIED reference CLI, with the CPU oracle standing in for the device plan.  The oracle is the
+checker's scorer here (tests only); the GPU twin of this test is tests/test_gpu_dropin.py."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import refloader  # noqa: E402
+sys.path.pop(0)
+
+pytestmark = pytest.mark.skipif(not refloader.available(), reason="reference package not available")
+
+
+class OraclePlan(object):
+    """The slice of engine.DevicePlan that demux_file uses, computed by oracle/qcat_oracle.c."""
+
+    def __init__(self, tables):
+        self.tables = tables
+
+    def detect(self, win5, tail3, wlen, read_len, subset=None, out=None):
+        got = helpers.oracle_detect(self.tables, win5, tail3, wlen, read_len, subset)
+        if out is not None:
+            out[...] = got
+            return out
+        return got
+
+    def kit_vote(self, win5, tail3, wlen):
+        return helpers.oracle_kit_vote(self.tables, win5, tail3, wlen)
+
+
+def _oracle_scanner(mode, kit, **kw):
+    from qcat_b200 import config, scanner
+    from qcat_b200.tables import Tables
+    cls = scanner.BarcodeScannerDual if mode == "dual" else scanner.BarcodeScannerEPI2ME
+    sc = cls(kit=kit, **kw)
+    plan = OraclePlan(Tables(sc.layouts, config.qcatConfig(), mode, sc.min_quality))
+    sc._plan_for = lambda qcat_config, layouts=None: plan
+    return sc
+
+
+def _run_cli(argv):
+    from qcat import cli
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(io.StringIO()):
+        cli.main(argv)
+    return out.getvalue()
+
+
+def _write_fastq(path, reads, qual_char="#"):
+    with open(path, "w") as fh:
+        for i, r in enumerate(reads):
+            fh.write("@read%d%s\n%s\n+\n%s\n" % (i, " ch=%d\tstart=%d" % (i % 512, i * 7) if i % 4 else "", r, qual_char * len(r)))
+
+
+@pytest.mark.parametrize("mode,kit,trim,filter_barcodes,n_reads", [
+    ("epi2me", "PBC096", True, False, 700),
+    ("epi2me", None, False, True, 4300),          # kit auto: per-batch vote over 12 layouts, two CLI batches
+    ("dual", None, True, False, 300),
+])
+def test_demux_file_matches_reference_cli(tmp_path, mode, kit, trim, filter_barcodes, n_reads):
+    refloader.load()
+    from qcat import scanner as ref_scanner
+    from qcat_b200 import fastx, synth
+    layouts = ref_scanner.factory(mode=mode, kit=kit or "RBK004").layouts if (kit or mode == "dual") else \
+        ref_scanner.factory(kit="RBK004").layouts
+    reads = synth.windows_to_reads(synth.generate(layouts, n_reads, seed=41, mean_len=700.0))
+    reads += ["", "ACGTN" * 70]
+    fastq = tmp_path / "reads.fastq"
+    _write_fastq(fastq, reads)
+    argv = ["-f", str(fastq), "--min-read-length", "120"] + (["-k", kit] if kit else []) + (["--trim"] if trim else [])
+    argv += (["--filter-barcodes"] if filter_barcodes else []) + (["--dual"] if mode == "dual" else [])
+    stream_cpu = _run_cli(argv)
+    tsv_cpu = _run_cli(argv + ["--tsv", "-b", str(tmp_path / "cpu")])
+    files_cpu = {name: open(tmp_path / "cpu" / name).read() for name in sorted(os.listdir(tmp_path / "cpu"))}
+
+    sc = _oracle_scanner(mode, kit, enable_filter_barcodes=filter_barcodes)
+    stream, tsv = io.BytesIO(), io.StringIO()
+    first = fastx.demux_file(str(fastq), sc, trim=trim, min_read_length=120, output=stream, chunk_bytes=1 << 20)
+    second = fastx.demux_file(str(fastq), sc, trim=trim, min_read_length=120, tsv=tsv, out_dir=str(tmp_path / "native"),
+                              chunk_bytes=300000)
+    files_native = {name: open(tmp_path / "native" / name).read() for name in sorted(os.listdir(tmp_path / "native"))}
+    assert stream.getvalue().decode() == stream_cpu
+    assert tsv.getvalue() == tsv_cpu
+    assert files_native == files_cpu
+    assert first["reads"] == second["reads"] == len(reads)
+    assert first["barcodes"] == second["barcodes"] and sum(first["barcodes"].values()) == len(reads) - first["skipped"]
+    np.testing.assert_array_equal(first["records"], second["records"])
+
+
+def test_demux_file_propagates_errors(tmp_path):
+    """A malformed record deep inside the file and a failing scorer both surface as exceptions on the caller's thread
+    (no hang in the pipeline threads)."""
+    from qcat_b200 import fastx, synth
+    sc = _oracle_scanner("epi2me", "PBC096")
+    reads = synth.windows_to_reads(synth.generate(sc.layouts, 600, seed=2, mean_len=600.0))
+    good = tmp_path / "good.fastq"
+    _write_fastq(good, reads)
+    bad = tmp_path / "bad.fastq"
+    text = good.read_text().split("\n")
+    text[4 * 400 + 3] = text[4 * 400 + 3][:-3]                      # quality shorter than the sequence in record 400
+    bad.write_text("\n".join(text))
+    with pytest.raises(fastx.FastxError):
+        fastx.demux_file(str(bad), sc, chunk_bytes=100000)
+
+    class Boom(RuntimeError):
+        pass
+
+    def explode(*args, **kwargs):
+        raise Boom("scorer failed")
+    sc._plan_for(None).detect = explode
+    with pytest.raises(Boom):
+        fastx.demux_file(str(good), sc, chunk_bytes=100000)
+    with pytest.raises(IOError):
+        fastx.demux_file(str(tmp_path / "missing.fastq"), sc)
