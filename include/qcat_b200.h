@@ -101,7 +101,8 @@ const char *qcb_version(void);
 qcb_plan *qcb_plan_create(const qcb_tables *tables, int device);
 void      qcb_plan_destroy(qcb_plan *plan);
 int       qcb_plan_info(qcb_plan *plan, qcb_plan_info_t *out);
-/* 0 = automatic (fast kernels when the scoring scheme allows), 1 = force the generic kernels. */
+/* 0 = automatic (fast kernels when the scoring scheme allows), 1 = force the generic kernels, 2 = generic kernels
+ * without the row-chunked adapter stage of long qcb_scan windows (one thread per window x template; cross-check). */
 int       qcb_plan_set_force_generic(qcb_plan *plan, int force);
 
 /* Per-stage device timing (CUDA events around each pipeline stage on the launching stream).  Off by default.

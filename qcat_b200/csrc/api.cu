@@ -60,6 +60,7 @@ struct qcb_plan {
     int device = 0;
     int sm_count = 0;
     bool force_generic = false;
+    bool no_row_chunks = false;      // force level 2: long windows on one thread per (window, template), as a cross-check
     DevTables t{};
     void *slab = nullptr;            // device tables
     size_t slab_bytes = 0;
@@ -68,7 +69,8 @@ struct qcb_plan {
     int max_adapter = 0, max_template = 0;
     FastPlan fast;                   // packed-kernel tables (kernels_fast.cuh)
     // workspace, sized per chunk of reads
-    DeviceBuffer wins, codes, ad_score, ad_end, sel, bc_score, subset_dev, misc;
+    DeviceBuffer wins, codes, ad_score, ad_end, sel, bc_score, subset_dev, misc, long_part, long_row;
+    int long_ov = 0;                 // warm-up rows of k_adapter_long (0 = chunking not provably exact for these tables)
     cudaStream_t stream = nullptr;   // kernels of the host-buffer entry points
     cudaStream_t copy_in = nullptr, copy_out = nullptr;      // H2D / D2H of the host-buffer entry points
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -84,6 +86,8 @@ struct qcb_plan {
 };
 
 namespace {
+
+constexpr int kLongChunkRows = 1024;   // rows per chunk of k_adapter_long
 
 template <typename T>
 size_t slab_put(std::vector<uint8_t> &slab, const T *src, size_t count)
@@ -152,6 +156,18 @@ int upload_tables(qcb_plan *p, const qcb_tables *h)
         }
     }
     for (int b = 0; b < nt; ++b) p->max_template = std::max(p->max_template, h->tmpl_off[b + 1] - h->tmpl_off[b]);
+    {
+        // k_adapter_long's warm-up length: m (1 + (smax - smin) / gmin) + 1 rows for the longest adapter
+        int smax = INT32_MIN, smin = INT32_MAX, max_alen = 0;
+        for (int i = 0; i < h->amat_size * h->amat_size; ++i) { smax = std::max(smax, h->amat[i]); smin = std::min(smin, h->amat[i]); }
+        for (int L = 0; L < nl; ++L) max_alen = std::max(max_alen, h->adapter_off[L + 1] - h->adapter_off[L]);
+        const int gmin = std::min(h->adapter_open, h->adapter_extend);
+        p->long_ov = 0;
+        if (gmin > 0 && smax >= smin) {
+            const long long ov = (long long)max_alen + ((long long)max_alen * (smax - smin) + gmin - 1) / gmin + 1;
+            if (ov < (1 << 20)) p->long_ov = (int)ov;
+        }
+    }
     return 0;
 }
 
@@ -236,6 +252,19 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
         adapter_rc = fast_adapter_stage(p->fast, t, (const uint8_t *)p->codes.ptr, stride, d_wlen, wshift, nw, h_subset, n_subset,
                                         ad_score, ad_end, st, &p->launches);
         if (adapter_rc == 1) return fail("fast adapter stage launch failed");
+    }
+    if (adapter_rc == 2 && window_mode && !p->no_row_chunks && p->long_ov > 0 && stride >= 2 * kLongChunkRows) {
+        // long windows (--detect-middle): rows in parallel chunks, see k_adapter_long
+        const int nch = (stride + kLongChunkRows - 1) / kLongChunkRows;
+        if (p->long_part.reserve((size_t)nw * n_subset * nch * sizeof(LongPart))) return 1;
+        if (p->long_row.reserve((size_t)nw * n_subset * sizeof(int2))) return 1;
+        k_adapter_long<<<grid_for(nw * n_subset * nch, 128), 128, 0, st>>>(t, wins, stride, d_wlen, nw, d_subset, n_subset, kLongChunkRows,
+                                                                         p->long_ov, nch, (LongPart *)p->long_part.ptr, (int2 *)p->long_row.ptr);
+        k_adapter_long_combine<<<grid_for(nw * n_subset, 128), 128, 0, st>>>(t, d_wlen, nw, d_subset, n_subset, nch,
+                                                                            (const LongPart *)p->long_part.ptr, (const int2 *)p->long_row.ptr,
+                                                                            ad_score, ad_end);
+        p->launches += 2;
+        adapter_rc = 0;
     }
     if (adapter_rc == 2) {
         if (packed_only) return fail("internal: packed adapter stage unavailable after the ASCII windows were skipped");
@@ -466,6 +495,7 @@ int qcb_plan_set_force_generic(qcb_plan *p, int force)
 {
     if (!p) return fail("plan is NULL");
     p->force_generic = force != 0;
+    p->no_row_chunks = force == 2;
     return 0;
 }
 

@@ -116,6 +116,92 @@ __global__ void k_adapter_generic(DevTables t, const uint8_t *__restrict__ wins,
     ad_score[id] = sc; ad_end[id] = eq;
 }
 
+// ---- long windows (--detect-middle scans read[W:-W], scanner_base.py:479-519) -----------------------------------------
+// One thread per (window, template) walks tens of thousands of rows serially.  Rows are therefore cut into chunks that
+// run in parallel: chunk c owns rows (c CH, (c+1) CH] and starts its DP `ov` rows earlier from an all-zero row (the
+// state of a window that begins there).  With every matrix entry in [smin, smax] and every gap character costing at
+// least gmin > 0, a path that reaches a cell more than ov = m (1 + (smax - smin) / gmin) rows below its start scores less
+// than the pure-diagonal path every cell has (>= smin m), so it never decides a maximum: all cells of the owned rows are
+// exact, and the per-chunk results below combine to exactly sg_affine's answer.
+struct LongPart {
+    int32_t col_max, col_arg;        // max of H[i][m] over the chunk's own rows, first row attaining it (1-based, global)
+};
+
+__global__ void k_adapter_long(DevTables t, const uint8_t *__restrict__ wins, int stride, const int32_t *__restrict__ wlen,
+                               long long n_windows, const int32_t *__restrict__ subset, int n_subset, int CH, int ov, int nch,
+                               LongPart *__restrict__ part, int2 *__restrict__ last_row)
+{
+    __shared__ int32_t s_mat[kMaxMatrix * kMaxMatrix];
+    __shared__ uint8_t s_map[256];
+    load_matrix_smem(s_mat, s_map, t.amat, t.amat_size, t.amap);
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_windows * n_subset * nch) return;
+    const int c = (int)(id % nch);
+    const long long ws = id / nch;                   // (window, subset entry)
+    const long long w = ws / n_subset;
+    const int L = subset[(int)(ws % n_subset)];
+    const int n = wlen[w];
+    const int own = c * CH;                          // rows (own, end] belong to this chunk
+    if (own >= n && !(n <= 0 && c == 0)) { part[id].col_max = INT32_MIN; part[id].col_arg = -1; return; }
+    const uint8_t *ref = t.adapter_seq + t.adapter_off[L];
+    const int m = t.adapter_off[L + 1] - t.adapter_off[L];
+    if (n <= 0 || m <= 0) { part[id].col_max = INT32_MIN; part[id].col_arg = -1; last_row[ws] = make_int2(INT32_MIN, -1); return; }
+    const int end = min(n, own + CH);
+    const int start = max(0, own - ov);
+    const uint8_t *q = wins + w * stride;
+    const int open = t.a_open, extend = t.a_extend, msize = t.amat_size;
+    int32_t H[kMaxTemplate + 1];
+    int32_t F[kMaxTemplate + 1];
+    uint8_t rc[kMaxTemplate];
+    for (int j = 0; j < m; ++j) rc[j] = s_map[ref[j]];
+    for (int j = 0; j <= m; ++j) { H[j] = 0; F[j] = kNegInf; }
+    int col_max = INT32_MIN, col_arg = -1;
+    for (int i = start + 1; i <= end; ++i) {
+        const int32_t *row = s_mat + msize * s_map[q[i - 1]];
+        int diag = 0, left = 0, E = kNegInf;
+        for (int j = 1; j <= m; ++j) {
+            int up = H[j];
+            int f = max(F[j] - extend, up - open);
+            int e = max(E - extend, left - open);
+            int h = max(max(diag + row[rc[j - 1]], e), f);
+            F[j] = f; E = e; diag = up; H[j] = h; left = h;
+        }
+        if (i > own && left > col_max) { col_max = left; col_arg = i; }
+    }
+    part[id].col_max = col_max; part[id].col_arg = col_arg;
+    if (end == n) {                                  // the chunk holding the last row also reports its maximum
+        int row_max = INT32_MIN, row_arg = -1;
+        for (int j = 1; j <= m; ++j)
+            if (H[j] > row_max) { row_max = H[j]; row_arg = j; }
+        last_row[ws] = make_int2(row_max, row_arg);
+    }
+}
+
+// sg_affine's end-cell rule over the chunk results of one (window, template).
+__global__ void k_adapter_long_combine(DevTables t, const int32_t *__restrict__ wlen, long long n_windows,
+                                       const int32_t *__restrict__ subset, int n_subset, int nch,
+                                       const LongPart *__restrict__ part, const int2 *__restrict__ last_row,
+                                       int32_t *__restrict__ ad_score, int32_t *__restrict__ ad_end)
+{
+    const long long ws = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ws >= n_windows * n_subset) return;
+    const long long w = ws / n_subset;
+    const int L = subset[(int)(ws % n_subset)];
+    const int n = wlen[w];
+    const int m = t.adapter_off[L + 1] - t.adapter_off[L];
+    if (n <= 0 || m <= 0) { ad_score[ws] = 0; ad_end[ws] = -1; return; }
+    int col_max = INT32_MIN, col_arg = -1;
+    for (int c = 0; c < nch; ++c) {
+        const LongPart p = part[ws * nch + c];
+        if (p.col_arg >= 0 && p.col_max > col_max) { col_max = p.col_max; col_arg = p.col_arg; }
+    }
+    const int2 r = last_row[ws];
+    int score, end;
+    if (col_max > r.x) { score = col_max; end = col_arg - 1; }
+    else { score = r.x; end = n - 1; if (r.y == m) end = col_arg - 1; }
+    ad_score[ws] = score; ad_end[ws] = end;
+}
+
 // Python slice semantics seq[start:stop] -> [lo, hi).
 __device__ __forceinline__ void py_slice(int start, int stop, int n, int &lo, int &hi)
 {

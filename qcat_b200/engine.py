@@ -88,7 +88,7 @@ class DevicePlan(object):
         return {name: getattr(out, name) for name, _ in out._fields_}
 
     def set_force_generic(self, force):
-        _ffi.check(self._lib.qcb_plan_set_force_generic(self._handle, 1 if force else 0))
+        _ffi.check(self._lib.qcb_plan_set_force_generic(self._handle, int(force)))
 
     STAGES = ("orient", "adapter", "select", "barcode", "decide", "context")
 

@@ -102,3 +102,59 @@ def test_scan_single_window_and_truncating_zip():
     # detect_barcode_batch(read_qualities=[None]) silently truncates to one read (scanner_base.py:714, :723)
     assert len(sc.detect_barcode_batch([window, window, window])) == 1
     assert sc.detect_barcode_batch([]) == []
+
+
+@pytest.mark.parametrize("mode,kit", [("epi2me", "PBC096"), ("epi2me", "VMK001"), ("epi2me", None), ("dual", None)])
+def test_long_window_row_chunks_equal_single_thread_scan(mode, kit):
+    """qcb_scan on long windows (--detect-middle bodies): the row-chunked adapter stage (k_adapter_long, 1024-row chunks
+    with a provably sufficient warm-up) gives exactly the records of the one-thread-per-template generic kernel, with
+    adapters planted at and across chunk boundaries, at the window ends, and in windows of every chunk-count."""
+    from qcat_b200 import config, engine, scanner
+    from qcat_b200.tables import Tables
+    rng = np.random.default_rng(17)
+    sc = scanner.factory(mode=mode, kit=kit, device=0)
+    tables = Tables(sc.layouts, config.qcatConfig(), mode, sc.min_quality)
+    plan = engine.DevicePlan(tables, device=0)
+
+    def noisy(seq):
+        out = []
+        for ch in seq:
+            r = rng.random()
+            if r < 0.03:
+                continue
+            out.append("ACGT"[rng.integers(4)] if r < 0.07 else ch)
+            if rng.random() < 0.02:
+                out.append("ACGT"[rng.integers(4)])
+        return "".join(out)
+
+    windows = []
+    for length in [0, 1, 500, 1023, 1024, 1025, 2047, 2048, 2049, 3000, 4096, 5000, 7777]:
+        for rep in range(6):
+            body = list("".join("ACGT"[i] for i in rng.integers(0, 4, size=length)))
+            if length > 200 and rep:
+                layout = sc.layouts[int(rng.integers(len(sc.layouts)))]
+                bc = layout.barcode_set_1[int(rng.integers(len(layout.barcode_set_1)))].sequence
+                adapter = layout.get_adapter_sequences(bc)
+                if layout.is_double_barcode():
+                    bc2 = layout.barcode_set_2[int(rng.integers(len(layout.barcode_set_2)))].sequence
+                    p2 = layout.barcode_pos_2
+                    adapter = adapter[:p2.start] + bc2 + adapter[p2.end + 1:]
+                adapter = noisy(adapter) if rep > 2 else adapter
+                # around every chunk boundary, at both ends, and somewhere random
+                anchors = [1024 * k for k in range(1, length // 1024 + 1)] + [0, length - len(adapter), int(rng.integers(0, length))]
+                pos = int(anchors[int(rng.integers(len(anchors)))] - rng.integers(0, len(adapter) + 1))
+                pos = max(0, min(pos, length - len(adapter)))
+                body[pos:pos + len(adapter)] = list(adapter)
+                if rep == 5:                                        # a second copy: ties between far-apart rows
+                    pos2 = max(0, min(int(rng.integers(0, length)), length - len(adapter)))
+                    body[pos2:pos2 + len(adapter)] = list(adapter)
+            windows.append("".join(body)[:length] if length else "")
+    subset = list(range(len(sc.layouts)))
+    plan.set_force_generic(1)
+    chunked = plan.scan_windows(windows, subset)
+    plan.set_force_generic(2)
+    serial = plan.scan_windows(windows, subset)
+    plan.set_force_generic(0)
+    helpers.assert_records_equal(chunked, serial, "row-chunked vs single-thread scan")
+    assert (serial["layout"] >= 0).sum() > len(windows) // 3
+    plan.close()
