@@ -27,6 +27,38 @@ __device__ __forceinline__ void decode_task(long long t, long long n_windows, in
     if (dual && t >= n_windows) { w = t - n_windows; k = 1; } else { w = t; k = 0; }
 }
 
+// Task order of the barcode stage.  A tile of 32 tasks runs as many rows as its longest region, so tasks are bucketed by
+// region length first: short regions (extract_barcode_region: barcode + 2 x extension + 1 rows) from slot 0 upwards,
+// long ones (the full-window branch, or a Python slice that wraps around) from the last slot downwards.  Slots are
+// handed out with warp-aggregated atomics; the order inside a bucket is irrelevant (every task writes its own scores).
+__global__ void k_task_order(DevTables t, const WindowSel *__restrict__ sel, long long n_windows, int dual, int short_rows,
+                             unsigned int *__restrict__ counters, uint32_t *__restrict__ perm)
+{
+    const long long n_tasks = dual ? 2 * n_windows : n_windows;
+    const long long task = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = task < n_tasks;
+    long long w; int k;
+    decode_task(valid ? task : 0, n_windows, dual, w, k);
+    const WindowSel s = sel[w];
+    int n = k ? s.hi1 - s.lo1 : s.hi0 - s.lo0;
+    if (t.group[s.layout * 2 + k] < 0 || n < 0) n = 0;
+    const bool is_long = n >= short_rows;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned m_short = __ballot_sync(0xffffffffu, valid && !is_long), m_long = __ballot_sync(0xffffffffu, valid && is_long);
+    unsigned base_short = 0, base_long = 0;
+    if (lane == 0) {
+        if (m_short) base_short = atomicAdd(&counters[0], (unsigned)__popc(m_short));
+        if (m_long) base_long = atomicAdd(&counters[1], (unsigned)__popc(m_long));
+    }
+    base_short = __shfl_sync(0xffffffffu, base_short, 0);
+    base_long = __shfl_sync(0xffffffffu, base_long, 0);
+    if (!valid) return;
+    const unsigned below = (1u << lane) - 1u;
+    const long long slot = is_long ? n_tasks - 1 - (long long)(base_long + __popc(m_long & below))
+                                   : (long long)(base_short + __popc(m_short & below));
+    perm[slot] = (uint32_t)task;
+}
+
 // Shared-context columns.  F[i] = H[i][u] + (i+u) g for the forward DP of region rows vs the shared prefix;
 // G[i] = H'[n-i][d] + (n-i+d) g for the DP of the reversed region vs the reversed shared suffix, whose left border
 // is 0 except -g at its last row (node (0, m) is not a valid end).  See DESIGN.md section 4.
@@ -40,8 +72,8 @@ constexpr int kCtxWarps = 4;
 template <int NCOL>
 __global__ void __launch_bounds__(kCtxWarps * 32)
 k_context(FastDev f, DevTables t, const uint32_t *__restrict__ ctx_tab, const uint8_t *__restrict__ codes, int stride,
-          long long n_windows, const WindowSel *__restrict__ sel, int dual, uint32_t *__restrict__ rowinfo,
-          int4 *__restrict__ taskmeta)
+          long long n_windows, const WindowSel *__restrict__ sel, int dual, const uint32_t *__restrict__ perm,
+          uint32_t *__restrict__ rowinfo, int4 *__restrict__ taskmeta)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -55,10 +87,11 @@ k_context(FastDev f, DevTables t, const uint32_t *__restrict__ ctx_tab, const ui
     const long long n_tasks = dual ? 2 * n_windows : n_windows;
     const long long n_tiles = (n_tasks + kRowTile - 1) / kRowTile;
     for (long long tile = (long long)blockIdx.x * kCtxWarps + warp; tile < n_tiles; tile += (long long)gridDim.x * kCtxWarps) {
-        const long long task = tile * kRowTile + lane;
-        const bool valid = task < n_tasks;
+        const long long slot = tile * kRowTile + lane;          // position in the bucketed task order (k_task_order)
+        const bool valid = slot < n_tasks;
+        const long long task = valid ? (long long)perm[slot] : 0;
         long long w; int k;
-        decode_task(valid ? task : 0, n_windows, dual, w, k);
+        decode_task(task, n_windows, dual, w, k);
         const WindowSel s = sel[w];
         const int lo = k ? s.lo1 : s.lo0, hi = k ? s.hi1 : s.hi0;
         const int grp = t.group[s.layout * 2 + k];
@@ -138,7 +171,7 @@ k_context(FastDev f, DevTables t, const uint32_t *__restrict__ ctx_tab, const ui
             }
         }
         __syncwarp();
-        if (valid) taskmeta[task] = make_int4(n, grp, rup, 0);
+        if (valid) taskmeta[slot] = make_int4(n, grp, rup, (int)task);
     }
 }
 
@@ -178,9 +211,12 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr)
 // one LOP3 for the profile address (see kRowCodeMask), a pointer-compare loop, diagonal terms issued one column ahead
 // of the in-place max chain so that no register copies are needed.
 __global__ void __launch_bounds__(kBarcodeWarps * 32, 3)
-k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots,
+k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, int rows_min, int rows_cap,
                const uint32_t *__restrict__ rowinfo, const int4 *__restrict__ taskmeta, int32_t *__restrict__ bc_score)
 {
+    // rows_cap = DP rows (0..n) the shared-memory row tile of this launch holds; a tile is taken when its longest region
+    // satisfies rows_min <= n < rows_cap, so a plan whose regions are almost always short (dual mode) can run them with a
+    // small tile (three CTAs per SM) and leave the rare long ones to a second launch with the full tile.
     extern __shared__ __align__(1024) uint8_t smem_bc[];
     uint8_t *smem = smem_bc;
     uint32_t *s_prof = (uint32_t *)smem;                             // [pair][code][kProfRowBytes], 1 KB per pair
@@ -204,7 +240,7 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots,
         const FastGroup G = f.groups[meta.y < 0 ? 0 : meta.y];
         int n = meta.y < 0 ? 0 : meta.x;
         const int nmax = __reduce_max_sync(0xffffffffu, n);
-        if (__syncthreads_or(nmax > 0) == 0) continue;               // tile has nothing for this kernel
+        if (__syncthreads_or(nmax >= rows_min && nmax < rows_cap) == 0) continue;   // nothing here for this launch
         {
             const uint32_t *src = rowinfo + tile * (long long)(kRows * kRowTile);
             const int words = (nmax + 1) * kRowTile;
@@ -212,7 +248,7 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots,
         }
         __syncthreads();
         long long w; int k;
-        decode_task(task < n_tasks ? task : 0, n_windows, dual, w, k);
+        decode_task((long long)(uint32_t)meta.w, n_windows, dual, w, k);      // the task behind this slot
         const int rup = meta.z;
         const int npairs = (G.nb + 1) >> 1;
         const int npairs_max = __reduce_max_sync(0xffffffffu, n > 0 ? npairs : 0);

@@ -70,11 +70,15 @@ struct FastPlan {
     int sm_count = 0;
     size_t barcode_smem = 0;
     int max_pairs = 1;               // barcode pairs of the largest template group
+    int short_rows = 0;              // > 0: row-tile size of the first of two k_barcode_fast launches (dual mode)
+    int bucket_rows = kRows;         // regions shorter than this go to the front of the task order (k_task_order)
     const uint32_t *ctx_tab = nullptr;   // device: k_context score tables
     int ctx_ncol = 12;
     size_t context_smem = 0;
     void *rowinfo = nullptr;         // [tiles][kRows][32] u32: code row offset | F << 10 | G << 21 (kernels_barcode_fast.cuh)
-    void *taskmeta = nullptr;        // [tasks] int4 {region length, group, R over prefix columns, -}
+    void *taskmeta = nullptr;        // [slots] int4 {region length, group, R over prefix columns, task}
+    void *perm = nullptr;            // [slots] u32 task of every slot (k_task_order), followed by the two bucket counters
+    size_t perm_bytes = 0;
     size_t rowinfo_bytes = 0, taskmeta_bytes = 0;
     // adapter stage: host copies used to build per-subset profiles
     int a_gap = 0, a_codes = 0;
@@ -84,7 +88,7 @@ struct FastPlan {
     std::vector<AdapterSubset *> subsets;
     size_t workspace_bytes() const
     {
-        size_t b = slab_bytes + rowinfo_bytes + taskmeta_bytes;
+        size_t b = slab_bytes + rowinfo_bytes + taskmeta_bytes + perm_bytes;
         for (auto *sub : subsets) b += sub->bytes;
         return b;
     }
@@ -251,7 +255,8 @@ inline void fast_plan_free(FastPlan &fp)
     fp.slab = nullptr; fp.slab_bytes = 0;
     if (fp.rowinfo) cudaFree(fp.rowinfo);
     if (fp.taskmeta) cudaFree(fp.taskmeta);
-    fp.rowinfo = fp.taskmeta = nullptr; fp.rowinfo_bytes = fp.taskmeta_bytes = 0;
+    if (fp.perm) cudaFree(fp.perm);
+    fp.rowinfo = fp.taskmeta = fp.perm = nullptr; fp.rowinfo_bytes = fp.taskmeta_bytes = fp.perm_bytes = 0;
     for (auto *sub : fp.subsets) { if (sub->dev) cudaFree(sub->dev); delete sub; }
     fp.subsets.clear();
 }
@@ -410,6 +415,17 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     fp.dev.n_codes = nc;
     fp.dev.gap = g;
     fp.dev.n_groups = ng;
+    // Rows of a region: the whole window on the epi2me full-window branch, otherwise barcode + 2 x extension + 1
+    // (extract_barcode_region) -- except for the odd end_query whose Python slice wraps around.  Dual mode always
+    // extracts, so it runs a first launch with a small row tile and a second one (full tile) for the exceptions.
+    fp.short_rows = 0;
+    {
+        int longest = 0;
+        for (int i = 0; i < h->n_layouts * 2; ++i) longest = std::max(longest, h->bc_len[i]);
+        const int rows = longest + 2 * std::max(0, h->barcode_extension) + 2;
+        fp.bucket_rows = std::min(rows, kRows);
+        if (h->mode == QCB_MODE_DUAL && rows < kRows / 2) fp.short_rows = rows;
+    }
     fp.barcode_smem = profile_bytes + (size_t)kRows * kRowTile * 4;
     if (fp.barcode_smem > 220 * 1024) return 0;
     if (cudaFuncSetAttribute(k_barcode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.barcode_smem) != cudaSuccess ||
@@ -520,15 +536,29 @@ inline int fast_context_stage(FastPlan &fp, const DevTables &t, const uint8_t *c
         if (cudaMalloc(&fp.taskmeta, need_meta + need_meta / 8) != cudaSuccess) return 1;
         fp.taskmeta_bytes = need_meta + need_meta / 8;
     }
+    const size_t need_perm = (size_t)n_tiles * kRowTile * 4 + 16;
+    if (need_perm > fp.perm_bytes) {
+        if (fp.perm) cudaFree(fp.perm);
+        fp.perm = nullptr; fp.perm_bytes = 0;
+        if (cudaMalloc(&fp.perm, need_perm + need_perm / 8) != cudaSuccess) return 1;
+        fp.perm_bytes = need_perm + need_perm / 8;
+    }
     uint32_t *rowinfo = (uint32_t *)fp.rowinfo;
     int4 *taskmeta = (int4 *)fp.taskmeta;
+    uint32_t *perm = (uint32_t *)fp.perm;
+    unsigned int *counters = (unsigned int *)((uint8_t *)fp.perm + (size_t)n_tiles * kRowTile * 4);
+    {
+        if (cudaMemsetAsync(counters, 0, 8, st) != cudaSuccess) return 1;
+        k_task_order<<<(unsigned)((n_tasks + 255) / 256), 256, 0, st>>>(t, sel, n_windows, dual, fp.bucket_rows, counters, perm);
+        ++*launches;
+    }
     {
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / fp.context_smem));
         const int cgrid = (int)std::min<long long>((n_tiles + kCtxWarps - 1) / kCtxWarps, (long long)fp.sm_count * per_sm);
         if (fp.ctx_ncol == 12)
-            k_context<12><<<cgrid, kCtxWarps * 32, fp.context_smem, st>>>(fp.dev, t, fp.ctx_tab, codes, stride, n_windows, sel, dual, rowinfo, taskmeta);
+            k_context<12><<<cgrid, kCtxWarps * 32, fp.context_smem, st>>>(fp.dev, t, fp.ctx_tab, codes, stride, n_windows, sel, dual, perm, rowinfo, taskmeta);
         else
-            k_context<16><<<cgrid, kCtxWarps * 32, fp.context_smem, st>>>(fp.dev, t, fp.ctx_tab, codes, stride, n_windows, sel, dual, rowinfo, taskmeta);
+            k_context<16><<<cgrid, kCtxWarps * 32, fp.context_smem, st>>>(fp.dev, t, fp.ctx_tab, codes, stride, n_windows, sel, dual, perm, rowinfo, taskmeta);
         ++*launches;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
@@ -553,11 +583,18 @@ inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, long long n_wind
             if (waste < best_waste) { best_waste = waste; warps = wc; }
         }
         const size_t regs_per_cta = (size_t)warps * 32 * 80;
-        int ctas_per_sm = (int)std::min<size_t>((220 * 1024) / std::max<size_t>(1, fp.barcode_smem), 65536 / regs_per_cta);
-        ctas_per_sm = std::max(1, std::min(ctas_per_sm, 8));
-        int grid = (int)std::min<long long>(n_tiles, (long long)fp.sm_count * ctas_per_sm);
-        k_barcode_fast<<<grid, warps * 32, fp.barcode_smem, st>>>(fp.dev, n_windows, dual, bmax0, bslots, rowinfo, taskmeta, bc_score);
-        ++*launches;
+        const size_t profile_bytes = fp.barcode_smem - (size_t)kRows * kRowTile * 4;
+        const int passes = fp.short_rows > 0 ? 2 : 1;
+        for (int pass = 0; pass < passes; ++pass) {
+            const int rows_min = pass == 0 ? 1 : fp.short_rows;
+            const int rows_cap = (passes == 2 && pass == 0) ? fp.short_rows : kRows;
+            const size_t smem = profile_bytes + (size_t)rows_cap * kRowTile * 4;
+            int ctas_per_sm = (int)std::min<size_t>((220 * 1024) / std::max<size_t>(1, smem), 65536 / regs_per_cta);
+            ctas_per_sm = std::max(1, std::min(ctas_per_sm, 8));
+            int grid = (int)std::min<long long>(n_tiles, (long long)fp.sm_count * ctas_per_sm);
+            k_barcode_fast<<<grid, warps * 32, smem, st>>>(fp.dev, n_windows, dual, bmax0, bslots, rows_min, rows_cap, rowinfo, taskmeta, bc_score);
+            ++*launches;
+        }
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
