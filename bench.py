@@ -24,6 +24,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_RESULT_FD = None
+
+
+def emit_result(line):
+    """Write the result line to the process's original stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 ALGORITHMIC_BYTES_PER_READ = 336     # SURVEY.md 8(d): 2 x 150 B windows + 4 B length in, one 32 B record out
 CONFIG_INDEX = 2                     # BASELINE.json configs[2]: 96 barcodes, 1 -> 8 GPUs
 KIT = "PBC096"                       # the reference's 96-barcode EPI2ME kit (NBD196 does not exist in qcat 1.1.0)
@@ -164,7 +177,7 @@ def run_reference(args):
                              "note": "reference = pure Python over parasail (not installable offline); this is the C oracle "
                                      "port of that path, scalar int32 affine DP, OpenMP over reads"},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit_result(line)
     return 0
 
 
@@ -382,7 +395,7 @@ def run_ours(args):
                 "config": workload_config(args, n), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "compute_roofline": compute, "cpu_baseline": cpu, "parity": parity,
                 "kernels": {"fast_adapter": info["fast_adapter"], "fast_barcode": info["fast_barcode"]}}
-        print(json.dumps(line))
+        emit_result(line)
     plan.close()
     if world > 1:
         dist.destroy_process_group()
@@ -390,6 +403,12 @@ def run_ours(args):
 
 
 def main():
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when
+    # NCCL_DEBUG is set in the environment), so everything but the final line is sent to stderr at file-descriptor level.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     kit, mode, _ = WORKLOADS[args.workload]
     if args.mode is None:
