@@ -86,6 +86,8 @@ struct FastPlan {
     std::vector<uint8_t> a_map;
     std::vector<std::vector<uint8_t>> a_seq;       // per layout adapter sequence (ASCII)
     std::vector<AdapterSubset *> subsets;
+    bool adapter_smem_configured[3] = {false, false, false};   // k_adapter_fast<NC> opted into full dynamic shared memory
+    int smem_optin = 0;              // cudaDevAttrMaxSharedMemoryPerBlockOptin of the plan's device
     size_t workspace_bytes() const
     {
         size_t b = slab_bytes + rowinfo_bytes + taskmeta_bytes + perm_bytes;
@@ -428,11 +430,20 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     }
     fp.barcode_smem = profile_bytes + (size_t)kRows * kRowTile * 4;
     if (fp.barcode_smem > 220 * 1024) return 0;
-    if (cudaFuncSetAttribute(k_barcode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.barcode_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_context<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.context_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_context<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.context_smem) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
+    // Opt every packed kernel into the device's full dynamic shared memory once.  The attribute is a per-device, per-
+    // kernel maximum shared by all plans of the process, so it must never be lowered to one plan's own need.
+    {
+        int dev = 0, optin = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+        if ((size_t)optin < fp.barcode_smem || (size_t)optin < fp.context_smem) return 0;
+        fp.smem_optin = optin;
+        if (cudaFuncSetAttribute(k_barcode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess ||
+            cudaFuncSetAttribute(k_context<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess ||
+            cudaFuncSetAttribute(k_context<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
     }
     fp.barcode_ok = true;
     return 0;
@@ -482,10 +493,14 @@ inline int launch_adapter_fast(FastPlan &fp, AdapterSubset *sub, const uint8_t *
                                long long n_windows, int n_subset, int32_t *ad_score, int32_t *ad_end, cudaStream_t st)
 {
     const size_t smem = sub->profile_bytes + (size_t)kAdapterWarps * kRows * kTile;
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(k_adapter_fast<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-        configured = smem;
+    // opt into the device's full dynamic shared memory (a per-device, per-kernel maximum shared by all plans: never lower it)
+    bool &configured = fp.adapter_smem_configured[NC <= 48 ? 0 : (NC <= 64 ? 1 : 2)];
+    if (!configured) {
+        int dev = 0, optin = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 1;
+        if (cudaFuncSetAttribute(k_adapter_fast<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) return 1;
+        configured = true;
     }
     const long long n_tiles = (n_windows + kTile - 1) / kTile;
     const long long n_tasks = n_tiles * sub->npairs;

@@ -158,3 +158,23 @@ def test_long_window_row_chunks_equal_single_thread_scan(mode, kit):
     helpers.assert_records_equal(chunked, serial, "row-chunked vs single-thread scan")
     assert (serial["layout"] >= 0).sum() > len(windows) // 3
     plan.close()
+
+
+def test_plans_of_different_kits_coexist():
+    """Several plans in one process (the scanner caches up to four): the packed kernels' dynamic shared-memory opt-in is
+    a per-device maximum shared by all of them, so creating a small-kit plan must not break a large-kit one."""
+    from qcat_b200 import config, engine, scanner, synth
+    from qcat_b200.tables import Tables
+    made = []
+    for mode, kit in (("epi2me", "PBC096"), ("epi2me", "NBD103/NBD104"), ("dual", None), ("epi2me", None)):
+        sc = scanner.factory(mode=mode, kit=kit, device=0)
+        tables = Tables(sc.layouts, config.qcatConfig(), mode, sc.min_quality)
+        data = synth.generate(sc.layouts if (kit or mode == "dual") else scanner.factory(kit="RBK004").layouts, 700, seed=5)
+        made.append((engine.DevicePlan(tables, device=0), tables, data))
+    for _ in range(2):
+        for plan, tables, data in made + made[::-1]:
+            got = plan.detect(data["win5"], data["tail3"], data["wlen"], data["read_len"])
+            want = helpers.oracle_detect(tables, data["win5"], data["tail3"], data["wlen"], data["read_len"])
+            helpers.assert_records_equal(got, want, "interleaved plans")
+    for plan, _, _ in made:
+        plan.close()
