@@ -347,7 +347,7 @@ def run_ours(args):
             compute["smem_gather_roofline"] = {"kernel": "k_barcode_fast", "unit": "shared-memory wavefronts/s",
                                                "wavefronts_per_read": wavefronts_per_read, "achieved": achieved_wf,
                                                "peak": peak_wf, "frac": achieved_wf / peak_wf,
-                                               "evidence": "profiles/r01c_barcode_full.md"}
+                                               "evidence": "profiles/r01d_barcode_full.md"}
 
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside) ------------
     e2e = None
