@@ -66,30 +66,28 @@ void parallel_for(int64_t n, int threads, F fn)
     for (auto &th : pool) th.join();
 }
 
-// copy up to `want` sequence characters starting at p (forward), skipping line breaks
-inline int copy_forward(const char *p, const char *end, uint8_t *dst, int want)
+// Characters [a, b) of a record's sequence (or quality) whose lines lie in [s, e): every line contributes its characters
+// without trailing whitespace, exactly what the indexer counted (Bio's parsers join line.rstrip() pieces).
+inline uint8_t *copy_bases(uint8_t *o, const char *s, const char *e, int64_t a, int64_t b)
 {
-    int k = 0;
-    while (k < want && p < end) {
-        const char c = *p++;
-        if (c == '\n' || c == '\r') continue;
-        dst[k++] = (uint8_t)c;
+    int64_t pos = 0;
+    const char *p = s;
+    while (p < e && pos < b) {
+        const char *le = line_end(p, e);
+        const int64_t k = rstrip_len(p, le);
+        const int64_t lo = std::max<int64_t>(a - pos, 0), hi = std::min<int64_t>(b - pos, k);
+        if (hi > lo) { memcpy(o, p + lo, (size_t)(hi - lo)); o += hi - lo; }
+        pos += k;
+        p = le < e ? le + 1 : e;
     }
-    return k;
+    return o;
 }
 
-// the last `want` sequence characters of [begin, end), in read order
-inline int copy_tail(const char *begin, const char *end, uint8_t *dst, int want)
+// characters [a, b) of a sequence / quality span: one memcpy for single-line records, line by line for wrapped ones
+inline uint8_t *put_span(uint8_t *o, const char *span, int64_t span_bytes, int64_t n_chars, int64_t a, int64_t b)
 {
-    int k = 0;
-    const char *p = end;
-    while (k < want && p > begin) {
-        const char c = *--p;
-        if (c == '\n' || c == '\r') continue;
-        dst[want - 1 - k++] = (uint8_t)c;
-    }
-    if (k < want) memmove(dst, dst + (want - k), (size_t)k);
-    return k;
+    if (span_bytes == n_chars) { memcpy(o, span + a, (size_t)(b - a)); return o + (b - a); }
+    return copy_bases(o, span, span + span_bytes, a, b);
 }
 
 // Serial record scan of [start, end); offsets are relative to `base`.  `final_chunk`: the range ends the input (a last
@@ -352,9 +350,9 @@ int qcb_pack_windows(const char *buf, const qcb_fastx_record *recs, int64_t n, i
             if (r.seq_span == r.seq_len) {                         // single line: plain copies
                 memcpy(h, s, (size_t)k);
                 memcpy(t, e - k, (size_t)k);
-            } else {
-                copy_forward(s, e, h, k);
-                copy_tail(s, e, t, k);
+            } else {                                               // wrapped record: line by line
+                copy_bases(h, s, e, 0, k);
+                copy_bases(t, s, e, r.seq_len - k, r.seq_len);
             }
             wlen[i] = k;
             read_len[i] = r.seq_len;
@@ -379,7 +377,6 @@ int qcb_format_records(const char *buf, const qcb_fastx_record *recs, const qcb_
     for (int64_t i = 0; i < n; ++i) {
         const qcb_fastx_record &r = recs[i];
         if (bin[i] < 0 || bin[i] >= n_bins) return io_fail("bin[%lld] out of range", (long long)i);
-        if (r.seq_span != r.seq_len || (fastq && r.qual_span != r.seq_len)) return io_fail("multi-line records are not supported by the native writer");
         int64_t a = 0, b = r.seq_len;
         if (trim) {                                                 // Python slice semantics of seq[trim5p:trim3p]
             a = std::min<int64_t>(std::max<int64_t>(results[i].trim5p, 0), r.seq_len);
@@ -422,11 +419,11 @@ int qcb_format_records(const char *buf, const qcb_fastx_record *recs, const qcb_
             }
             if (!blank) *o++ = ' ';
             *o++ = '\n';
-            memcpy(o, buf + r.seq_off + a, (size_t)(b - a)); o += b - a;
+            o = put_span(o, buf + r.seq_off, r.seq_span, r.seq_len, a, b);
             *o++ = '\n';
             if (fastq) {
                 *o++ = '+'; *o++ = '\n';
-                memcpy(o, buf + r.qual_off + a, (size_t)(b - a)); o += b - a;
+                o = put_span(o, buf + r.qual_off, r.qual_span, r.seq_len, a, b);
                 *o++ = '\n';
             }
         }
@@ -486,7 +483,6 @@ int qcb_format_stream(const char *buf, const qcb_fastx_record *recs, const qcb_r
     for (int64_t i = 0; i < n; ++i) {
         const qcb_fastx_record &r = recs[i];
         if (label[i] < 0 || label[i] >= n_labels) return io_fail("label[%lld] out of range", (long long)i);
-        if (r.seq_span != r.seq_len || (fastq && r.qual_span != r.seq_len)) return io_fail("multi-line records are not supported by the native writer");
     }
     parallel_for(n, threads, [&](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
@@ -523,11 +519,11 @@ int qcb_format_stream(const char *buf, const qcb_fastx_record *recs, const qcb_r
             const int64_t l0 = label_off[label[i]], l1 = label_off[label[i] + 1];
             memcpy(o, labels + l0, (size_t)(l1 - l0)); o += l1 - l0;
             *o++ = '\n';
-            memcpy(o, buf + r.seq_off + c.a, (size_t)(c.b - c.a)); o += c.b - c.a;
+            o = put_span(o, buf + r.seq_off, r.seq_span, r.seq_len, c.a, c.b);
             *o++ = '\n';
             if (fastq) {
                 *o++ = '+'; *o++ = '\n';
-                memcpy(o, buf + r.qual_off + c.a, (size_t)(c.b - c.a)); o += c.b - c.a;
+                o = put_span(o, buf + r.qual_off, r.qual_span, r.seq_len, c.a, c.b);
                 *o++ = '\n';
             }
         }

@@ -281,3 +281,64 @@ def test_stream_and_tsv_writers_match_cli_layout():
         assert lib.qcb_format_tsv(vp(arr), vp(recs), vp(results), vp(tsv_label), vp(kit_label), n, vp(blob), vp(off), len(strings),
                                   trim, min_len, vp(out), cap, ctypes.byref(need), vp(kept), 4) == 0
         assert out[:need.value].tobytes().decode() == want_tsv.getvalue()
+
+
+def test_writers_handle_wrapped_records():
+    """qcb_format_records / qcb_format_stream on wrapped FASTQ (80 columns) and CRLF input cut [trim5p:trim3p] in base
+    coordinates, line breaks skipped."""
+    import ctypes
+    from qcat_b200 import _ffi
+    reads = _random_reads(120, 12, max_len=700)
+    for layout in ("wrapped", "crlf"):
+        if layout == "wrapped":
+            wrap = lambda t: "".join(t[j:j + 80] + "\n" for j in range(0, len(t), 80)) or "\n"
+            buf = "".join("@%s\n%s+\n%s" % (t, wrap(s), wrap(q)) for t, s, q in reads).encode()
+        else:
+            buf = _fastq_bytes(reads, crlf=True)
+        recs, _, _ = fastx.index_buffer(buf)
+        n = len(recs)
+        assert n == len(reads)
+        rng = np.random.default_rng(4)
+        results = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+        lens = np.array([len(s) for _, s, _ in reads])
+        results["trim5p"] = rng.integers(0, 120, size=n)
+        results["trim3p"] = np.maximum(lens - rng.integers(0, 120, size=n), 0)
+        strings = ["none", "3"]
+        blob = np.frombuffer(b"none3\0", dtype=np.uint8)
+        off = np.array([0, 4, 5], dtype=np.int64)
+        label = rng.integers(0, 2, size=n).astype(np.int32)
+        lib = _ffi.load()
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        kept = np.zeros(n, dtype=np.uint8)
+        need = ctypes.c_int64(0)
+        args = (vp(arr), vp(recs), vp(results), vp(label), n, vp(blob), vp(off), 2, 1, 1, 30)
+        assert lib.qcb_format_stream(*args, None, 0, ctypes.byref(need), vp(kept), 3) == 0
+        out = np.zeros(need.value + 1, dtype=np.uint8)
+        assert lib.qcb_format_stream(*args, vp(out), int(out.size), ctypes.byref(need), vp(kept), 3) == 0
+        want = io.StringIO()
+        for i, (title, seq, qual) in enumerate(reads):
+            seq, qual = seq[results["trim5p"][i]:results["trim3p"][i]], qual[results["trim5p"][i]:results["trim3p"][i]]
+            if len(seq) < 30:
+                continue
+            cols = title.replace("\t", " ").split(" ")
+            name, comment = cols[0], (" ".join(cols[1:]) if len(cols) > 1 else None)
+            print("@" + name + " " + "{} barcode={}".format(comment or "", strings[label[i]]), seq, "+", qual, sep="\n", file=want)
+        assert out[:need.value].tobytes().decode() == want.getvalue()
+        bin_bytes = np.zeros(2, dtype=np.int64); bin_off = np.zeros(2, dtype=np.int64)
+        rargs = (vp(arr), vp(recs), vp(results), vp(label), n, 2, 1, 1, 30, vp(bin_bytes))
+        assert lib.qcb_format_records(*rargs, None, 0, vp(bin_off), vp(kept), 3) == 0
+        out = np.zeros(int(bin_bytes.sum()) + 1, dtype=np.uint8)
+        assert lib.qcb_format_records(*rargs, vp(out), int(out.size), vp(bin_off), vp(kept), 3) == 0
+        for b in range(2):
+            want = io.StringIO()
+            for i, (title, seq, qual) in enumerate(reads):
+                if label[i] != b:
+                    continue
+                seq, qual = seq[results["trim5p"][i]:results["trim3p"][i]], qual[results["trim5p"][i]:results["trim3p"][i]]
+                if len(seq) < 30:
+                    continue
+                cols = title.replace("\t", " ").split(" ")
+                name, comment = cols[0], (" ".join(cols[1:]) if len(cols) > 1 else None)
+                print("@" + name + " " + (comment or ""), seq, "+", qual, sep="\n", file=want)
+            assert out[bin_off[b]:bin_off[b] + bin_bytes[b]].tobytes().decode() == want.getvalue()

@@ -95,6 +95,37 @@ def test_demux_file_matches_reference_cli(tmp_path, mode, kit, trim, filter_barc
     np.testing.assert_array_equal(first["records"], second["records"])
 
 
+@pytest.mark.parametrize("fmt", ["fasta_wrapped", "fastq_crlf"])
+def test_demux_file_other_input_layouts(tmp_path, fmt):
+    """Wrapped FASTA (the usual 60-column layout) and CRLF line ends go through the same native reader, window packing
+    and writers; output must equal the reference CLI's (Bio's parsers join the rstrip()ped lines).  Wrapped FASTQ is
+    covered natively in tests/test_fastx.py only: the Bio stand-in of oracle/refshim reads four-line records."""
+    refloader.load()
+    from qcat import scanner as ref_scanner
+    from qcat_b200 import fastx, synth
+    layouts = ref_scanner.factory(kit="PBC096").layouts
+    reads = synth.windows_to_reads(synth.generate(layouts, 400, seed=43, mean_len=500.0)) + ["ACGT" * 20, "A"]
+    path = tmp_path / ("reads.fasta" if fmt.startswith("fasta") else "reads.fastq")
+    with open(path, "w", newline="") as fh:
+        for i, r in enumerate(reads):
+            if fmt == "fasta_wrapped":
+                fh.write(">read%d desc=%d\n" % (i, i) + "".join(r[j:j + 60] + "\n" for j in range(0, len(r), 60)))
+            else:
+                fh.write("@read%d x\r\n%s\r\n+\r\n%s\r\n" % (i, r, "5" * len(r)))
+    argv = ["-f", str(path), "-k", "PBC096", "--trim", "--min-read-length", "50"]
+    stream_cpu = _run_cli(argv)
+    tsv_cpu = _run_cli(argv + ["--tsv", "-b", str(tmp_path / "cpu")])
+    files_cpu = {name: open(tmp_path / "cpu" / name).read() for name in sorted(os.listdir(tmp_path / "cpu"))}
+    sc = _oracle_scanner("epi2me", "PBC096")
+    stream, tsv = io.BytesIO(), io.StringIO()
+    fastx.demux_file(str(path), sc, trim=True, min_read_length=50, output=stream, chunk_bytes=70000)
+    fastx.demux_file(str(path), sc, trim=True, min_read_length=50, tsv=tsv, out_dir=str(tmp_path / "native"), chunk_bytes=1 << 20)
+    files_native = {name: open(tmp_path / "native" / name).read() for name in sorted(os.listdir(tmp_path / "native"))}
+    assert stream.getvalue().decode() == stream_cpu
+    assert tsv.getvalue() == tsv_cpu
+    assert files_native == files_cpu and len(files_native) > 5
+
+
 def test_demux_file_propagates_errors(tmp_path):
     """A malformed record deep inside the file and a failing scorer both surface as exceptions on the caller's thread
     (no hang in the pipeline threads)."""
