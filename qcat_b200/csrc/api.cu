@@ -372,7 +372,10 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
     }
     QCB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = p->stream, s_in = p->copy_in, s_out = p->copy_out;
-    long long chunk = std::min<long long>(p->chunk_reads, p->host_chunk_reads);
+    // Pipeline granularity: at least 64 Ki reads per chunk (small kernels lose time in their last wave of tiles), larger
+    // for big calls as long as ~8 chunks remain to overlap the copies with the kernels, never above the device chunk.
+    long long chunk = std::max<long long>(p->host_chunk_reads, (n_reads / 8 + 31) / 32 * 32);
+    chunk = std::min<long long>(chunk, p->chunk_reads);
     if ((long long)stride * chunk > (1LL << 27)) chunk = std::max<long long>(1, (1LL << 27) / stride);
     const size_t out_item = vote ? 4 : sizeof(qcb_result);
     int rc = 0;
