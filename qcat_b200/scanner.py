@@ -11,7 +11,6 @@ classes have, so qcat_b200.dropin can graft it onto an installed qcat.
 import logging
 import operator
 
-import numpy as np
 
 from qcat_b200 import adapters
 from qcat_b200 import config

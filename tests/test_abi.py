@@ -3,7 +3,6 @@ import ctypes
 import os
 import re
 
-import numpy as np
 import pytest
 
 ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))

@@ -1,6 +1,5 @@
 """Native FASTQ / FASTA ingest (qcb_fastx_index, qcb_pack_windows, qcb_format_records) against plain Python."""
 import io
-import os
 import random
 
 import numpy as np

@@ -5,7 +5,6 @@ import io
 import os
 import sys
 
-import numpy as np
 import pytest
 
 ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))

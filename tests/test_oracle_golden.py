@@ -1,5 +1,4 @@
 """CPU: the C oracle (oracle/qcat_oracle.c) reproduces the reference's Python results stored in tests/golden."""
-import numpy as np
 import pytest
 
 from tests import helpers

@@ -5,7 +5,6 @@
 Writes a synthetic FASTQ to /tmp, then times (a) reading + indexing + window packing alone (1 thread / all cores),
 (b) demux_file without outputs, (c) with the TSV table, (d) with trimmed per-barcode FASTQ output, (e) kit auto.
 File I/O goes through the page cache."""
-import io
 import json
 import os
 import sys

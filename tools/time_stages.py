@@ -1,7 +1,7 @@
 """Per-stage device timing of one plan on synthetic reads (no parity check): python tools/time_stages.py [kit] [n_reads]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from qcat_b200 import config, engine, scanner, synth
 from qcat_b200.tables import Tables
 
