@@ -13,6 +13,7 @@ import ctypes
 import io
 import os
 import queue
+import sys
 import threading
 
 import numpy as np
@@ -457,10 +458,12 @@ def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min
     consumer = threading.Thread(target=consume, name="qcb-egress", daemon=True)
     producer.start()
     consumer.start()
+    drained = False
     try:
         while True:
             item = packed_q.get()
             if item is _STOP:
+                drained = True
                 break
             chunk, packed = item
             if failure:
@@ -476,6 +479,13 @@ def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min
                 all_records.append(results)
             scored_q.put((chunk, packed[3], results))
     finally:
+        if not drained:                                        # interrupted while waiting: let the reader thread finish
+            failure.append(sys.exc_info()[1] or RuntimeError("demux_file aborted"))
+            while True:
+                item = packed_q.get()
+                if item is _STOP:
+                    break
+                item[0].release()
         scored_q.put(_STOP)
         consumer.join()
         done.set()
