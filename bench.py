@@ -44,6 +44,8 @@ KIT = "PBC096"                       # the reference's 96-barcode EPI2ME kit (NB
 WORKLOADS = {
     "configs[1]": ("NBD103/NBD104", "epi2me", "12-barcode NBD104 kit"),
     "configs[2]": ("PBC096", "epi2me", "96-barcode PBC096 kit"),
+    "configs[2]-nbd196": ("NBD196", "epi2me", "synthetic 96-barcode EXP-NBD196 kit (NBD104 flanks + revcomp of the PBC096 "
+                                             "barcodes, tools/make_nbd196.py)"),
     "configs[3]": (None, "dual", "dual barcoding, 24 x 96 pairs (DUAL kit)"),
     "configs[4]": ("PBC096", "epi2me", "96-barcode PBC096 kit, --trim (trim offsets are part of every record)"),
 }
@@ -67,11 +69,15 @@ def parse_args():
     return ap.parse_args()
 
 
+NBD196_FOLDER = os.path.join(ROOT, "qcat_b200", "resources", "nbd196")
+
+
 def make_scanner_tables(kit, mode):
     from qcat_b200 import config, scanner
     from qcat_b200.tables import Tables
     cls = scanner.BarcodeScannerDual if mode == "dual" else scanner.BarcodeScannerEPI2ME
-    sc = cls(kit=kit)
+    # NBD196 is not a qcat kit: it is loaded from its own kit folder, like any custom kit (adapters.py:138-162)
+    sc = cls(kit=kit, kit_folder=NBD196_FOLDER if kit == "NBD196" else None)
     return sc, Tables(sc.layouts, config.qcatConfig(), mode, sc.min_quality)
 
 

@@ -43,7 +43,10 @@ def test_cuda_matches_reference_golden(golden, engine, case_index, force_generic
     plan.close()
 
 
-SYNTH = [("NBD103/NBD104", "epi2me", 20000), ("PBC096", "epi2me", 20000), ("RBK004", "epi2me", 4000),
+import os
+
+NBD196_FOLDER = os.path.join(helpers.ROOT, "qcat_b200", "resources", "nbd196")      # tools/make_nbd196.py (custom kit folder)
+SYNTH = [("NBD103/NBD104", "epi2me", 20000), ("PBC096", "epi2me", 20000), ("NBD196", "epi2me", 12000), ("RBK004", "epi2me", 4000),
          ("RAB204/RAB214", "epi2me", 4000), (None, "epi2me", 6000), ("dual", "dual", 8000), ("DUAL", "epi2me", 4000)]
 
 
@@ -53,7 +56,7 @@ def test_cuda_matches_oracle_on_synthetic(engine, kit, mode, n, force_generic):
     from qcat_b200 import config, scanner, synth
     from qcat_b200.tables import Tables
     cls = scanner.BarcodeScannerDual if mode == "dual" else scanner.BarcodeScannerEPI2ME
-    sc = cls(kit=None if kit == "dual" else kit)
+    sc = cls(kit=None if kit == "dual" else kit, kit_folder=NBD196_FOLDER if kit == "NBD196" else None)
     foreign = scanner.BarcodeScannerEPI2ME(kit="RBK001").layouts
     data = synth.generate(sc.layouts, n, seed=20261017 + n, foreign_layouts=foreign)
     tables = Tables(sc.layouts, config.qcatConfig(), mode, sc.min_quality)

@@ -186,3 +186,43 @@ def test_batch_record_conversion_equals_per_record(mode):
         assert a["adapter"] is b["adapter"] and type(a["barcode_score"]) is float and type(a["trim5p"]) is int
         if mode == "epi2me":
             assert a["barcode"] is b["barcode"]
+
+
+@needs_reference
+def test_custom_kit_folder_nbd196_matches_the_reference():
+    """BASELINE configs[2] names EXP-NBD196, which qcat 1.1.0 does not ship: the synthetic kit of tools/make_nbd196.py
+    is loaded through kit_folder by the reference (adapters.py:138-162) and by the mirror alike, and the oracle agrees
+    with the reference's Python on reads of that kit (batch and single-read API)."""
+    import os
+    refloader.load()
+    from qcat import config as ref_config
+    from qcat import scanner as ref_scanner
+    from qcat_b200 import config, scanner, synth
+    from qcat_b200.tables import Tables, pack_windows
+    folder = os.path.join(helpers.ROOT, "qcat_b200", "resources", "nbd196")
+    ref = ref_scanner.factory(kit="NBD196", kit_folder=folder)
+    mine = scanner.factory(kit="NBD196", kit_folder=folder)
+    assert sorted((l.kit, l.sequence, len(l.barcode_set_1)) for l in mine.layouts) == \
+        sorted((l.kit, l.sequence, len(l.barcode_set_1)) for l in ref.layouts)
+    assert len(mine.layouts) == 2 and all(len(l.barcode_set_1) == 96 for l in mine.layouts)
+    # same layout order as the reference object for the comparison (the folder glob is unsorted on both sides)
+    order = {l.sequence: i for i, l in enumerate(ref.layouts)}
+    mine.layouts.sort(key=lambda l: order[l.sequence])
+    data = synth.generate(mine.layouts, 160, seed=9, mean_len=900.0)
+    reads = synth.windows_to_reads(data) + ["", "ACGT", "N" * 400]
+    cfg = ref_config.qcatConfig()
+    want = ref.detect_barcode_batch(reads, [None] * len(reads), cfg)
+    tables = Tables(mine.layouts, config.qcatConfig(), "epi2me", mine.min_quality)
+    win5, tail3, wlen, read_len, _ = pack_windows(reads, 150)
+    got = helpers.oracle_detect(tables, win5, tail3, wlen, read_len)
+    assert sum(r["barcode"] is not None for r in want) > 100
+    assert len({r["barcode"].id for r in want if r["barcode"]}) > 40          # ids well beyond the 12 of NBD104
+    for g, w in zip(got, want):
+        if w["barcode"] is None:
+            assert g["barcode"] < 0 and g["exit_status"] == w["exit_status"]
+        else:
+            layout = mine.layouts[int(g["layout"])]
+            assert layout.sequence == w["adapter"].sequence
+            assert layout.barcode_set_1[int(g["barcode"])].id == w["barcode"].id
+            assert float(g["barcode_score"]) == w["barcode_score"] and int(g["adapter_end"]) == w["adapter_end"]
+        assert (int(g["trim5p"]), int(g["trim3p"])) == (w["trim5p"], w["trim3p"])
