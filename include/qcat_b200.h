@@ -186,7 +186,8 @@ int qcb_format_records(const char *buf, const qcb_fastx_record *recs, const qcb_
 /* Same as qcb_fastx_index with the scan spread over `threads` threads: the buffer is cut at record starts found by a
  * local test ('@' line, '+' two lines later, equal sequence / quality line lengths) that each neighbouring scan then
  * confirms by arriving exactly there; anything else (wrapped FASTQ, malformed input) falls back to the serial scan, so
- * results and errors are those of qcb_fastx_index. */
+ * results and errors are those of qcb_fastx_index.  Buffers under 1 MiB are scanned serially unless threads is negative
+ * (|threads| pieces whatever the size -- used by the tests to fuzz the cutting logic on small inputs). */
 int qcb_fastx_index_mt(const char *buf, int64_t len, int32_t final_chunk, qcb_fastx_record *recs, int64_t max_records,
                        int64_t *n_records, int64_t *consumed, int32_t *is_fastq, int32_t threads);
 

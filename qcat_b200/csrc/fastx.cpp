@@ -291,8 +291,9 @@ int index_from(const char *buf, const char *p, const char *end, bool fastq, bool
 {
     int rc = -1;
     *done = p;
-    if (threads > 1 && end - p >= (int64_t)1 << 20)
-        rc = index_parallel(buf, p, end, fastq, final_chunk, threads, recs, max_records, n_records, done);
+    // threads < 0: cut into |threads| pieces whatever the size (tests); otherwise only buffers worth the thread start-up
+    if (threads < -1 || (threads > 1 && end - p >= (int64_t)1 << 20))
+        rc = index_parallel(buf, p, end, fastq, final_chunk, threads < 0 ? -threads : threads, recs, max_records, n_records, done);
     if (rc < 0) rc = index_range(buf, p, end, fastq, final_chunk, recs, max_records, n_records, done);
     return rc;
 }

@@ -44,16 +44,20 @@ def index_buffer(buf, final_chunk=True, max_records=None, threads=1):
     Returns (records structured array, bytes consumed, is_fastq)."""
     lib = _ffi.load()
     arr = np.frombuffer(buf, dtype=np.uint8)
-    if max_records is None:
-        max_records = max(16, int(arr.size // 12) + 16)          # a record needs more than 12 bytes
-    recs = np.zeros(max_records, dtype=_ffi.RECORD_DTYPE)
     n = ctypes.c_int64(0)
     consumed = ctypes.c_int64(0)
     fastq = ctypes.c_int32(1)
-    if arr.size:
-        _check_io(lib.qcb_fastx_index_mt(_vp(arr), int(arr.size), 1 if final_chunk else 0, _vp(recs), int(max_records),
+    if not arr.size:
+        return np.zeros(0, dtype=_ffi.RECORD_DTYPE), 0, True
+    # without a limit from the caller the record array grows until the scan is no longer bounded by it
+    capacity = int(max_records) if max_records is not None else max(1024, int(arr.size // 64))
+    while True:
+        recs = np.zeros(capacity, dtype=_ffi.RECORD_DTYPE)
+        _check_io(lib.qcb_fastx_index_mt(_vp(arr), int(arr.size), 1 if final_chunk else 0, _vp(recs), capacity,
                                          ctypes.byref(n), ctypes.byref(consumed), ctypes.byref(fastq), int(threads)))
-    return recs[:n.value], int(consumed.value), bool(fastq.value)
+        if max_records is not None or n.value < capacity:
+            return recs[:n.value], int(consumed.value), bool(fastq.value)
+        capacity *= 4
 
 
 def pack_windows(buf, recs, max_align_length=150, threads=None):
