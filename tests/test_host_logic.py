@@ -226,3 +226,63 @@ def test_custom_kit_folder_nbd196_matches_the_reference():
             assert layout.barcode_set_1[int(g["barcode"])].id == w["barcode"].id
             assert float(g["barcode_score"]) == w["barcode_score"] and int(g["adapter_end"]) == w["adapter_end"]
         assert (int(g["trim5p"]), int(g["trim3p"])) == (w["trim5p"], w["trim3p"])
+
+
+def test_vectorised_batch_kit_vote_equals_reference_rule():
+    """fastx._batch_kits (numpy, per CLI batch) picks the same kit as the reference's dict-insertion-order + stable-sort
+    rule (scanner_base.py:657-678, mirrored by GpuScannerMixin._kit_from_votes), ties included."""
+    from qcat_b200 import fastx
+    from qcat_b200.scanner import GpuScannerMixin
+    rng = np.random.default_rng(11)
+    names = ["A", "A", "B", "C", "C", "C", "D"]                         # layouts -> kits
+    kit_names = list(dict.fromkeys(names))
+    kit_of_layout = np.array([kit_names.index(k) for k in names], dtype=np.int64)
+    for trial in range(200):
+        n = int(rng.integers(1, 60))
+        batch = int(rng.integers(1, 12))
+        vote = rng.integers(0, len(names), size=n).astype(np.int32)
+        if trial % 3 == 0:                                               # force ties
+            vote = np.resize(rng.permutation(len(names)), n).astype(np.int32)
+        got = fastx._batch_kits(vote, kit_of_layout, len(kit_names), batch)
+        want = [GpuScannerMixin._kit_from_votes(vote[lo:lo + batch], names) for lo in range(0, n, batch)]
+        assert [kit_names[k] for k in got] == want
+
+
+def test_vectorised_filter_barcodes_equals_reference_rule():
+    """fastx._filter_barcodes == BarcodeScanner.filter_barcodes per batch (scanner_base.py:680-712): ids seen in
+    <= int(5 % of the most frequent key) reads are emptied, 'none' counts as a key, trims are reset."""
+    from qcat_b200 import _ffi, config, fastx, scanner
+    from qcat_b200.tables import Tables
+    sc = scanner.BarcodeScannerEPI2ME(kit="PBC096")
+    tables = Tables(sc.layouts, config.qcatConfig(), "epi2me", sc.min_quality)
+
+    class FakePlan(object):
+        pass
+    plan = FakePlan()
+    plan.tables = tables
+    rng = np.random.default_rng(5)
+    n, batch = 900, 300
+    recs = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+    weights = np.r_[np.full(6, 0.15), np.full(90, 0.1 / 90)]            # six frequent barcodes, a long tail of rare ones
+    recs["barcode"] = rng.choice(96, size=n, p=weights / weights.sum())
+    recs["layout"] = rng.integers(0, 2, size=n)
+    none = rng.random(n) < 0.2
+    recs["layout"][none] = -1
+    recs["barcode"][none] = -1
+    recs["exit_status"] = np.where(none, 1, 0)
+    recs["barcode_score"] = np.where(none, 0.0, 77.0)
+    recs["trim5p"] = 30
+    recs["trim3p"] = 500
+    got = recs.copy()
+    fastx._filter_barcodes(tables, got, batch)
+    want = []
+    for lo in range(0, n, batch):
+        dicts = sc._records_to_dicts(plan, recs[lo:lo + batch])
+        count = {}
+        for d in dicts:
+            sc.update_barcode_count(d, count)
+        want += sc.filter_barcodes(count, dicts)
+    assert sum(w["barcode"] is None for w in want) > none.sum()          # something was filtered
+    for g, w in zip(got, want):
+        assert (g["barcode"] < 0) == (w["barcode"] is None)
+        assert (int(g["trim5p"]), int(g["trim3p"]), int(g["exit_status"])) == (w["trim5p"], w["trim3p"], w["exit_status"])
