@@ -213,7 +213,9 @@ int qcb_write_bins(const int32_t *fds, const uint8_t *out, const int64_t *bin_of
 /* Chunked reader replacing iter_fastx (cli.py:235-306) for files: qcb_reader_next() returns the next chunk of complete
  * records (bytes read with `threads` concurrent preads, indexed with qcb_fastx_index_mt); every chunk but the last holds
  * a multiple of `multiple_of` records so that CLI batches of 4000 stay aligned.  *chunk = NULL at the end of the file.
- * A chunk stays valid until qcb_chunk_release(); chunks may be released from another thread than the reading one. */
+ * A chunk stays valid until qcb_chunk_release(); chunks may be released from another thread than the reading one.
+ * path "-" = standard input (the CLI's default input, cli.py:256-259); anything that is not a regular file is read
+ * sequentially with read(). */
 typedef struct qcb_reader qcb_reader;
 typedef struct qcb_chunk qcb_chunk;
 qcb_reader *qcb_reader_open(const char *path, int64_t chunk_bytes, int32_t threads);

@@ -665,6 +665,7 @@ struct qcb_reader {
     int64_t chunk_bytes = 0;
     int threads = 1;
     bool eof = false;
+    bool stream = false;                     // not a regular file: read() sequentially until it returns 0
     qcb_chunk *pending = nullptr;            // next chunk's buffer; its first carry_len bytes follow the last record handed out
     int64_t carry_len = 0;
     std::vector<qcb_fastx_record> carry_recs;// records already indexed inside the carried bytes (offsets relative to their start)
@@ -677,13 +678,15 @@ struct qcb_reader {
 qcb_reader *qcb_reader_open(const char *path, int64_t chunk_bytes, int32_t threads)
 {
     if (!path) { io_fail("NULL argument"); return nullptr; }
-    const int fd = open(path, O_RDONLY);
+    const bool from_stdin = strcmp(path, "-") == 0;                 // the CLI reads stdin when no file is given (cli.py:256-259)
+    const int fd = from_stdin ? dup(0) : open(path, O_RDONLY);
     if (fd < 0) { io_fail("cannot open %s", path); return nullptr; }
     struct stat st;
     if (fstat(fd, &st) != 0) { close(fd); io_fail("cannot stat %s", path); return nullptr; }
     qcb_reader *rd = new qcb_reader();
     rd->fd = fd;
-    rd->file_size = (int64_t)st.st_size;
+    rd->stream = !S_ISREG(st.st_mode);                               // pipes, FIFOs, terminals: sequential read(), size unknown
+    rd->file_size = rd->stream ? INT64_MAX : (int64_t)st.st_size;
     rd->chunk_bytes = std::max<int64_t>(chunk_bytes, 4096);
     rd->threads = std::max(1, (int)threads);
     return rd;
@@ -754,7 +757,7 @@ int qcb_reader_next(qcb_reader *rd, int64_t multiple_of, qcb_chunk **chunk)
     for (;;) {
         if (rd->eof && rd->carry_len == 0) return 0;
         const int64_t want = std::min<int64_t>(rd->chunk_bytes, rd->file_size - rd->file_pos);
-        const int64_t total = rd->carry_len + want;
+        int64_t total = rd->carry_len + want;                          // (a stream may deliver less: corrected after the read)
         auto T0 = std::chrono::steady_clock::now();
         qcb_chunk *c = rd->pending;
         rd->pending = nullptr;
@@ -766,7 +769,16 @@ int qcb_reader_next(qcb_reader *rd, int64_t multiple_of, qcb_chunk **chunk)
         }
         char *dst = c->data + rd->carry_len;
         std::vector<int64_t> got((size_t)rd->threads, 0);
-        {
+        int64_t stream_got = -1;
+        if (rd->stream) {
+            stream_got = 0;
+            while (stream_got < want) {
+                const ssize_t k = read(rd->fd, dst + stream_got, (size_t)(want - stream_got));
+                if (k < 0) { if (errno == EINTR) continue; qcb_chunk_release(c); rd->carry_len = 0; return io_fail("read failed: %s", strerror(errno)); }
+                if (k == 0) { rd->eof = true; break; }
+                stream_got += k;
+            }
+        } else {
             const int64_t base = rd->file_pos;
             const int fd = rd->fd;
             int64_t *gp = got.data();
@@ -791,10 +803,12 @@ int qcb_reader_next(qcb_reader *rd, int64_t multiple_of, qcb_chunk **chunk)
         auto T1 = std::chrono::steady_clock::now();
         int64_t nread = 0;
         for (int64_t g : got) nread += g;
-        if (nread != want) { qcb_chunk_release(c); rd->carry_len = 0; return io_fail("short read"); }
-        rd->file_pos += want;
-        if (rd->file_pos >= rd->file_size) rd->eof = true;
+        if (rd->stream) nread = stream_got;
+        else if (nread != want) { qcb_chunk_release(c); rd->carry_len = 0; return io_fail("short read"); }
+        rd->file_pos += nread;
+        if (!rd->stream && rd->file_pos >= rd->file_size) rd->eof = true;
         const bool final_chunk = rd->eof;
+        total = rd->carry_len + nread;
         if (rd->fastq < 0) {
             const char *p0 = c->data, *e0 = c->data + total;
             while (p0 < e0 && (*p0 == '\n' || *p0 == '\r')) ++p0;

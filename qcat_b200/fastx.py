@@ -133,7 +133,8 @@ class Chunk(object):
 
 
 class Reader(object):
-    """Native chunked FASTQ / FASTA reader (qcb_reader_*): parallel pread + parallel record scan per chunk."""
+    """Native chunked FASTQ / FASTA reader (qcb_reader_*): parallel pread + parallel record scan per chunk.
+    path "-" (standard input), pipes and FIFOs are read sequentially."""
 
     def __init__(self, path, chunk_bytes=64 << 20, threads=None):
         self._lib = _ffi.load()
@@ -394,7 +395,8 @@ _STOP = object()
 
 def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min_read_length=0, out_dir=None, tsv=None,
                output=None, nobatch=False, chunk_bytes=None, threads=None, keep_records=True):
-    """Demultiplex a FASTQ / FASTA file like `qcat -f path [-b out_dir] [--tsv] [-o output] [--trim]` (cli.py:445-563).
+    """Demultiplex a FASTQ / FASTA file like `qcat -f path [-b out_dir] [--tsv] [-o output] [--trim]` (cli.py:445-563);
+    path "-" reads standard input, the CLI's default when no file is given.
 
     scanner: a qcat_b200 (or drop-in patched qcat) scanner.  Reads are scored in batches of `batch_size` (4000 in the
     CLI; `nobatch` = single-read mode without the kit vote).  out_dir: per-barcode files as with `-b`; tsv: a file

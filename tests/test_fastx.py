@@ -1,5 +1,6 @@
 """Native FASTQ / FASTA ingest (qcb_fastx_index, qcb_pack_windows, qcb_format_records) against plain Python."""
 import io
+import os
 import random
 
 import numpy as np
@@ -341,3 +342,30 @@ def test_writers_handle_wrapped_records():
                 name, comment = cols[0], (" ".join(cols[1:]) if len(cols) > 1 else None)
                 print("@" + name + " " + (comment or ""), seq, "+", qual, sep="\n", file=want)
             assert out[bin_off[b]:bin_off[b] + bin_bytes[b]].tobytes().decode() == want.getvalue()
+
+
+def test_reader_streams_from_stdin_and_fifos(tmp_path):
+    """path "-" = stdin (the CLI's default input, cli.py:256-259) and any non-regular file are read sequentially: same
+    chunks as from a regular file, including a record split across reads and a missing final newline."""
+    import subprocess
+    import sys
+    reads = _big_reads(1500, 21, "I5#@+")
+    data = _fastq_bytes(reads)[:-1]
+    path = tmp_path / "r.fastq"
+    path.write_bytes(data)
+    child = ("import sys; sys.path.insert(0, %r); from qcat_b200 import fastx\n"
+             "rd = fastx.Reader('-', 200000, threads=3); total = 0; lens = 0\n"
+             "for ch in rd.chunks(128):\n"
+             "    total += len(ch); lens += int(ch.recs['seq_len'].sum()); ch.release()\n"
+             "rd.close(); print(total, lens)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # through a pipe that delivers small pieces
+    feeder = subprocess.Popen([sys.executable, "-c", "import sys,time\nd=open(%r,'rb').read()\nfor i in range(0,len(d),70001):\n    sys.stdout.buffer.write(d[i:i+70001]); sys.stdout.buffer.flush()" % str(path)],
+                              stdout=subprocess.PIPE)
+    out = subprocess.run([sys.executable, "-c", child], stdin=feeder.stdout, capture_output=True, text=True, timeout=120)
+    feeder.wait()
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == [str(len(reads)), str(sum(len(s) for _, s, _ in reads))]
+    # redirected regular file on stdin takes the pread path
+    with open(path, "rb") as fh:
+        out = subprocess.run([sys.executable, "-c", child], stdin=fh, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.split()[0] == str(len(reads)), out.stderr
