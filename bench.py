@@ -158,6 +158,36 @@ def cpu_oracle_rate(tables, batch, sample, threads):
     return n / dt, n, res
 
 
+def reference_python_rate(args, batch, n_reads=1500):
+    """Reads/s of the UNMODIFIED reference Python (qcat.scanner.factory(...).detect_barcode_batch in CLI batches of 4000,
+    one process -- the reference has no other mode) over the parasail stand-in of oracle/refshim, on the first n_reads
+    reads of the batch.  None when the reference package did not travel to this box.  Never raises."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import refloader
+        sys.path.pop(0)
+        if not refloader.available():
+            return None
+        refloader.load()
+        from qcat import config as ref_config
+        from qcat import scanner as ref_scanner
+        from qcat_b200 import synth
+        kw = {"kit_folder": NBD196_FOLDER} if args.kit == "NBD196" else {}
+        sc = ref_scanner.factory(mode=args.mode, kit=args.kit, **kw)
+        n = min(n_reads, len(batch["wlen"]))
+        reads = synth.windows_to_reads({k: batch[k][:n] for k in batch})
+        cfg = ref_config.qcatConfig()
+        sc.detect_barcode_batch(reads[:50], [None] * 50, cfg)
+        t0 = time.perf_counter()
+        sc.detect_barcode_batch(reads, [None] * len(reads), cfg)
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "reads/s", "cores": 1,
+                "sample": "%d reads through the unmodified reference Python (detect_barcode_batch), its parasail calls served by "
+                          "the scalar C stand-in of oracle/refshim" % n}
+    except Exception as exc:                                   # noqa: BLE001 -- an extra number must not break the bench
+        return {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -181,7 +211,8 @@ def run_reference(args):
             "config": workload_config(args, args.cpu_sample),
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": sample,
                              "note": "reference = pure Python over parasail (not installable offline); this is the C oracle "
-                                     "port of that path, scalar int32 affine DP, OpenMP over reads"},
+                                     "port of that path, scalar int32 affine DP, OpenMP over reads",
+                             "reference_python": reference_python_rate(args, batch)},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_result(line)
     return 0
@@ -390,7 +421,8 @@ def run_ours(args):
             threads = os.cpu_count() or 1
             rate, m, _ = cpu_oracle_rate(tables, batch, args.cpu_sample, threads)
             cpu = {"value": rate, "unit": "reads/s", "cores": threads, "kind": "port",
-                   "sample": "first %d reads of the step batch, C oracle port (scalar int32 affine DP), OpenMP over reads" % m}
+                   "sample": "first %d reads of the step batch, C oracle port (scalar int32 affine DP), OpenMP over reads" % m,
+                   "reference_python": reference_python_rate(args, batch)}
 
     if rank == 0:
         info = plan.info()
