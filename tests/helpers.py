@@ -123,3 +123,23 @@ def assert_records_equal(got, want, what=""):
             i = int(bad[0])
             raise AssertionError("%s: field %s differs on %d/%d records; first at %d: got %r want %r" %
                                  (what, f, bad.size, len(want), i, got[i], want[i]))
+
+
+class OraclePlan(object):
+    """The slice of engine.DevicePlan the host layers use (tables, detect, kit_vote), computed by the CPU oracle: lets the
+    CPU suite drive qcat_b200.fastx.demux_file and the drop-in's Python glue without a GPU.  TESTS ONLY."""
+
+    def __init__(self, tables):
+        self.tables = tables
+        self.calls = 0
+
+    def detect(self, win5, tail3, wlen, read_len, subset=None, out=None):
+        self.calls += 1
+        got = oracle_detect(self.tables, win5, tail3, wlen, read_len, subset)
+        if out is not None:
+            out[...] = got
+            return out
+        return got
+
+    def kit_vote(self, win5, tail3, wlen):
+        return oracle_kit_vote(self.tables, win5, tail3, wlen)

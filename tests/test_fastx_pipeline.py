@@ -19,21 +19,7 @@ sys.path.pop(0)
 pytestmark = pytest.mark.skipif(not refloader.available(), reason="reference package not available")
 
 
-class OraclePlan(object):
-    """The slice of engine.DevicePlan that demux_file uses, computed by oracle/qcat_oracle.c."""
-
-    def __init__(self, tables):
-        self.tables = tables
-
-    def detect(self, win5, tail3, wlen, read_len, subset=None, out=None):
-        got = helpers.oracle_detect(self.tables, win5, tail3, wlen, read_len, subset)
-        if out is not None:
-            out[...] = got
-            return out
-        return got
-
-    def kit_vote(self, win5, tail3, wlen):
-        return helpers.oracle_kit_vote(self.tables, win5, tail3, wlen)
+OraclePlan = helpers.OraclePlan
 
 
 def _oracle_scanner(mode, kit, **kw):

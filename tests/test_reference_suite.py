@@ -21,17 +21,7 @@ HAVE_TESTS = os.path.isfile(os.path.join(refloader.REFERENCE_ROOT, "qcat", "test
 pytestmark = pytest.mark.skipif(not HAVE_TESTS, reason="reference checkout with its test-suite not available")
 
 
-class OraclePlan(object):
-    def __init__(self, tables):
-        self.tables = tables
-        self.calls = 0
-
-    def detect(self, win5, tail3, wlen, read_len, subset=None, out=None):
-        self.calls += 1
-        return helpers.oracle_detect(self.tables, win5, tail3, wlen, read_len, subset)
-
-    def kit_vote(self, win5, tail3, wlen):
-        return helpers.oracle_kit_vote(self.tables, win5, tail3, wlen)
+OraclePlan = helpers.OraclePlan
 
 
 def _reference_tests():
