@@ -481,10 +481,8 @@ int qcb_format_stream(const char *buf, const qcb_fastx_record *recs, const qcb_r
     if (n == 0) return 0;
     if (!buf || !recs || !results || !label || !labels || !label_off || !kept) return io_fail("NULL argument");
     std::vector<int64_t> pos((size_t)n + 1);
-    for (int64_t i = 0; i < n; ++i) {
-        const qcb_fastx_record &r = recs[i];
+    for (int64_t i = 0; i < n; ++i)
         if (label[i] < 0 || label[i] >= n_labels) return io_fail("label[%lld] out of range", (long long)i);
-    }
     parallel_for(n, threads, [&](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
             const qcb_fastx_record &r = recs[i];
