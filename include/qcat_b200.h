@@ -13,6 +13,10 @@
  *     batched over reads as in detect_barcode_batch (:714-733)              -> qcb_detect*()
  *   - detect_kit's per-read vote (scanner_base.py:618-678)                  -> qcb_kit_vote*()
  *   - the per-barcode counts behind the CLI histogram (cli.py:386-405)      -> qcb_histogram_device()
+ *   - host only, either side of the path: record iteration (cli.py:235-306), window extraction
+ *     (scanner_base.py:223-244), trimming / min-length filter and the three output forms
+ *     (cli.py:309-358, :408-442, :521-552)       -> qcb_reader_*(), qcb_fastx_index*(), qcb_pack_windows(),
+ *                                                   qcb_format_*(), qcb_write_bins()
  *
  * Conventions: plain pointers and sizes only; the caller owns every buffer; functions returning int
  * return 0 on success and non-zero on error, with a thread-local message in qcb_last_error(); nothing
