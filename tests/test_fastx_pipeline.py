@@ -77,6 +77,9 @@ def test_demux_file_matches_reference_cli(tmp_path, mode, kit, trim, filter_barc
     assert tsv.getvalue() == tsv_cpu
     assert files_native == files_cpu
     assert first["reads"] == second["reads"] == len(reads)
+    # `-o file`: output given as a path
+    fastx.demux_file(str(fastq), sc, trim=trim, min_read_length=120, output=str(tmp_path / "stream.out"), chunk_bytes=150000)
+    assert (tmp_path / "stream.out").read_text() == stream_cpu
     assert first["barcodes"] == second["barcodes"] and sum(first["barcodes"].values()) == len(reads) - first["skipped"]
     np.testing.assert_array_equal(first["records"], second["records"])
 
