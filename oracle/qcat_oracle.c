@@ -254,6 +254,28 @@ void qo_detect(const qo_tables *t, const uint8_t *win5, const uint8_t *tail3, in
     free(all);
 }
 
+/* BarcodeScanner.scan on stand-alone, already oriented windows of any length (what scan_middle feeds it,
+ * scanner_base.py:479-519): the per-window record before any two-end logic (trims 0, exit_status 0 / 1). */
+void qo_scan(const qo_tables *t, const uint8_t *windows, int64_t stride, const int32_t *wlen, int64_t n_windows,
+             const int32_t *subset, int n_subset, qo_result *out, int n_threads)
+{
+    (void)n_threads;
+    int32_t *all = 0;
+    if (!subset || n_subset <= 0) {
+        all = (int32_t *)malloc(sizeof(int32_t) * (size_t)(t->n_layouts > 0 ? t->n_layouts : 1));
+        for (int i = 0; i < t->n_layouts; ++i) all[i] = i;
+        subset = all; n_subset = t->n_layouts;
+    }
+#pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads > 0 ? n_threads : 1)
+    for (int64_t w = 0; w < n_windows; ++w) {
+        scan_result r = scan_window(t, subset, n_subset, windows + (size_t)w * (size_t)stride, wlen[w]);
+        out[w].layout = r.layout; out[w].barcode = r.barcode; out[w].barcode_score = r.score;
+        out[w].adapter_end = r.adapter_end; out[w].trim5p = 0; out[w].trim3p = 0;
+        out[w].exit_status = r.layout < 0 ? 1 : 0;
+    }
+    free(all);
+}
+
 void qo_kit_vote(const qo_tables *t, const uint8_t *win5, const uint8_t *tail3, int stride,
                  const int32_t *wlen, int64_t n_reads, int32_t *vote_layout, int n_threads)
 {

@@ -92,6 +92,12 @@ void qo_detect(const qo_tables *t, const uint8_t *win5, const uint8_t *tail3, in
                const int32_t *wlen, const int64_t *read_len, int64_t n_reads,
                const int32_t *subset, int n_subset, qo_result *out, int n_threads);
 
+/* BarcodeScanner.scan (scanner_epi2me.py:33-144 / scanner_dual.py:35-146) on n_windows already oriented windows of
+ * any length in slots of `stride` bytes: records with trims 0 and exit_status 0, or the empty record (layout -1,
+ * exit_status 1) where the reference returns empty_return_dict(). */
+void qo_scan(const qo_tables *t, const uint8_t *windows, int64_t stride, const int32_t *wlen, int64_t n_windows,
+             const int32_t *subset, int n_subset, qo_result *out, int n_threads);
+
 /* detect_kit's per-read vote (scanner_base.py:618-678): index of the layout of the higher-scoring end
  * over ALL layouts ("adapter_1" at :669). */
 void qo_kit_vote(const qo_tables *t, const uint8_t *win5, const uint8_t *tail3, int stride,

@@ -380,6 +380,13 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
     const size_t out_item = vote ? 4 : sizeof(qcb_result);
     int rc = 0;
     long long k = 0;
+    // errors inside the loop must still reach the stream synchronisations below: async copies on the caller's
+    // (pinned) buffers may be in flight
+#define LOOP_CUDA(call)                                                                                   \
+    {                                                                                                     \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) { rc = fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); break; } \
+    }
     for (long long off = 0; off < n_reads && !rc; off += chunk, ++k) {
         const int b = (int)(k & 1);
         long long n = std::min<long long>(chunk, n_reads - off);
@@ -388,32 +395,32 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
         size_t o_rl = o_len + (b_len + 255) / 256 * 256, total = o_rl + b_rl;
         // staging buffer b was last used by chunk k-2: its kernels and its D2H must be done before it is reused
         if (k >= 2) {
-            QCB_CUDA(cudaStreamWaitEvent(s_in, p->ev_compute[b], 0));
-            QCB_CUDA(cudaStreamWaitEvent(st, p->ev_d2h[b], 0));
+            LOOP_CUDA(cudaStreamWaitEvent(s_in, p->ev_compute[b], 0));
+            LOOP_CUDA(cudaStreamWaitEvent(st, p->ev_d2h[b], 0));
         }
         if (p->in_stage2[b].bytes < total || p->out_stage2[b].bytes < (size_t)n * out_item) {
-            QCB_CUDA(cudaDeviceSynchronize());             // growing a staging buffer frees memory still in flight
-            if (p->in_stage2[b].reserve(total)) return 1;
-            if (p->out_stage2[b].reserve((size_t)n * out_item)) return 1;
+            LOOP_CUDA(cudaDeviceSynchronize());             // growing a staging buffer frees memory still in flight
+            if (p->in_stage2[b].reserve(total) || p->out_stage2[b].reserve((size_t)n * out_item)) { rc = 1; break; }
         }
         uint8_t *d = (uint8_t *)p->in_stage2[b].ptr;
         void *d_res = p->out_stage2[b].ptr;
-        QCB_CUDA(cudaMemcpyAsync(d, win5 + off * stride, b_win, cudaMemcpyHostToDevice, s_in));
-        if (!window_mode) QCB_CUDA(cudaMemcpyAsync(d + o_tail, tail3 + off * stride, b_win, cudaMemcpyHostToDevice, s_in));
-        QCB_CUDA(cudaMemcpyAsync(d + o_len, wlen + off, b_len, cudaMemcpyHostToDevice, s_in));
-        if (!vote && !window_mode) QCB_CUDA(cudaMemcpyAsync(d + o_rl, read_len + off, b_rl, cudaMemcpyHostToDevice, s_in));
-        QCB_CUDA(cudaEventRecord(p->ev_h2d[b], s_in));
-        QCB_CUDA(cudaStreamWaitEvent(st, p->ev_h2d[b], 0));
+        LOOP_CUDA(cudaMemcpyAsync(d, win5 + off * stride, b_win, cudaMemcpyHostToDevice, s_in));
+        if (!window_mode) { LOOP_CUDA(cudaMemcpyAsync(d + o_tail, tail3 + off * stride, b_win, cudaMemcpyHostToDevice, s_in)); }
+        LOOP_CUDA(cudaMemcpyAsync(d + o_len, wlen + off, b_len, cudaMemcpyHostToDevice, s_in));
+        if (!vote && !window_mode) { LOOP_CUDA(cudaMemcpyAsync(d + o_rl, read_len + off, b_rl, cudaMemcpyHostToDevice, s_in)); }
+        LOOP_CUDA(cudaEventRecord(p->ev_h2d[b], s_in));
+        LOOP_CUDA(cudaStreamWaitEvent(st, p->ev_h2d[b], 0));
         rc = detect_device_impl(p, d, window_mode ? nullptr : d + o_tail, stride, (const int32_t *)(d + o_len),
                                 (const int64_t *)(d + o_rl), n, subset, n_subset, vote ? nullptr : (qcb_result *)d_res,
                                 vote ? (int32_t *)d_res : nullptr, st);
         if (rc) break;
-        QCB_CUDA(cudaEventRecord(p->ev_compute[b], st));
-        QCB_CUDA(cudaStreamWaitEvent(s_out, p->ev_compute[b], 0));
-        if (vote) QCB_CUDA(cudaMemcpyAsync(vote + off, d_res, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
-        else QCB_CUDA(cudaMemcpyAsync(out + off, d_res, (size_t)n * sizeof(qcb_result), cudaMemcpyDeviceToHost, s_out));
-        QCB_CUDA(cudaEventRecord(p->ev_d2h[b], s_out));
+        LOOP_CUDA(cudaEventRecord(p->ev_compute[b], st));
+        LOOP_CUDA(cudaStreamWaitEvent(s_out, p->ev_compute[b], 0));
+        if (vote) { LOOP_CUDA(cudaMemcpyAsync(vote + off, d_res, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out)); }
+        else { LOOP_CUDA(cudaMemcpyAsync(out + off, d_res, (size_t)n * sizeof(qcb_result), cudaMemcpyDeviceToHost, s_out)); }
+        LOOP_CUDA(cudaEventRecord(p->ev_d2h[b], s_out));
     }
+#undef LOOP_CUDA
     cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(s_out);
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
@@ -446,17 +453,17 @@ qcb_plan *qcb_plan_create(const qcb_tables *tables, int device)
     qcb_plan *p = new qcb_plan();
     p->device = device;
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { fail("cudaGetDeviceProperties failed"); delete p; return nullptr; }
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { fail("cudaGetDeviceProperties failed"); qcb_plan_destroy(p); return nullptr; }
     p->sm_count = prop.multiProcessorCount;
-    if (upload_tables(p, tables)) { delete p; return nullptr; }
+    if (upload_tables(p, tables)) { qcb_plan_destroy(p); return nullptr; }
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking) != cudaSuccess) { fail("stream creation failed"); delete p; return nullptr; }
+        cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking) != cudaSuccess) { fail("stream creation failed"); qcb_plan_destroy(p); return nullptr; }
     for (int i = 0; i < 2; ++i)
         if (cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&p->ev_compute[i], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&p->ev_d2h[i], cudaEventDisableTiming) != cudaSuccess) { fail("event creation failed"); delete p; return nullptr; }
-    if (fast_plan_build(p->fast, tables, p->sm_count)) { fail("fast-plan construction failed: %s", p->fast.error.c_str()); delete p; return nullptr; }
+            cudaEventCreateWithFlags(&p->ev_d2h[i], cudaEventDisableTiming) != cudaSuccess) { fail("event creation failed"); qcb_plan_destroy(p); return nullptr; }
+    if (fast_plan_build(p->fast, tables, p->sm_count)) { fail("fast-plan construction failed: %s", p->fast.error.c_str()); qcb_plan_destroy(p); return nullptr; }
     return p;
 }
 
@@ -466,7 +473,7 @@ void qcb_plan_destroy(qcb_plan *p)
     cudaSetDevice(p->device);
     fast_plan_free(p->fast);
     p->wins.release(); p->codes.release(); p->ad_score.release(); p->ad_end.release(); p->sel.release(); p->bc_score.release();
-    p->subset_dev.release(); p->misc.release();
+    p->subset_dev.release(); p->misc.release(); p->long_part.release(); p->long_row.release();
     if (p->slab) cudaFree(p->slab);
     for (int i = 0; i < 2; ++i) {
         p->in_stage2[i].release(); p->out_stage2[i].release();

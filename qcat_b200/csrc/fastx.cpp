@@ -66,28 +66,50 @@ void parallel_for(int64_t n, int threads, F fn)
     for (auto &th : pool) th.join();
 }
 
+// FASTA sequence lines: Bio's SimpleFastaParser joins line.rstrip() pieces and then removes every ' ' and '\r' that is
+// left inside (FastaIO.py: "".join(lines).replace(" ", "").replace("\r", "")), so such characters are not bases.
+inline bool fasta_blank(char c) { return c == ' ' || c == '\r'; }
+
+inline int64_t fasta_line_bases(const char *p, const char *q)
+{
+    int64_t k = rstrip_len(p, q);
+    const int64_t full = k;
+    for (int64_t i = 0; i < full; ++i) k -= fasta_blank(p[i]) ? 1 : 0;
+    return k;
+}
+
 // Characters [a, b) of a record's sequence (or quality) whose lines lie in [s, e): every line contributes its characters
-// without trailing whitespace, exactly what the indexer counted (Bio's parsers join line.rstrip() pieces).
-inline uint8_t *copy_bases(uint8_t *o, const char *s, const char *e, int64_t a, int64_t b)
+// without trailing whitespace, exactly what the indexer counted (Bio's parsers join line.rstrip() pieces); skip_blanks
+// (FASTA sequences) also drops blanks inside a line.
+inline uint8_t *copy_bases(uint8_t *o, const char *s, const char *e, int64_t a, int64_t b, bool skip_blanks = false)
 {
     int64_t pos = 0;
     const char *p = s;
     while (p < e && pos < b) {
         const char *le = line_end(p, e);
         const int64_t k = rstrip_len(p, le);
-        const int64_t lo = std::max<int64_t>(a - pos, 0), hi = std::min<int64_t>(b - pos, k);
-        if (hi > lo) { memcpy(o, p + lo, (size_t)(hi - lo)); o += hi - lo; }
-        pos += k;
+        if (skip_blanks && (memchr(p, ' ', (size_t)k) || memchr(p, '\r', (size_t)k))) {
+            for (int64_t i = 0; i < k && pos < b; ++i) {
+                if (fasta_blank(p[i])) continue;
+                if (pos >= a) *o++ = (uint8_t)p[i];
+                ++pos;
+            }
+        } else {
+            const int64_t lo = std::max<int64_t>(a - pos, 0), hi = std::min<int64_t>(b - pos, k);
+            if (hi > lo) { memcpy(o, p + lo, (size_t)(hi - lo)); o += hi - lo; }
+            pos += k;
+        }
         p = le < e ? le + 1 : e;
     }
     return o;
 }
 
 // characters [a, b) of a sequence / quality span: one memcpy for single-line records, line by line for wrapped ones
-inline uint8_t *put_span(uint8_t *o, const char *span, int64_t span_bytes, int64_t n_chars, int64_t a, int64_t b)
+inline uint8_t *put_span(uint8_t *o, const char *span, int64_t span_bytes, int64_t n_chars, int64_t a, int64_t b,
+                         bool skip_blanks = false)
 {
     if (span_bytes == n_chars) { memcpy(o, span + a, (size_t)(b - a)); return o + (b - a); }
-    return copy_bases(o, span, span + span_bytes, a, b);
+    return copy_bases(o, span, span + span_bytes, a, b, skip_blanks);
 }
 
 // Serial record scan of [start, end); offsets are relative to `base`.  `final_chunk`: the range ends the input (a last
@@ -123,7 +145,7 @@ int index_range(const char *base, const char *start, const char *end, bool fastq
             if (fastq ? *p == '+' : *p == '>') { complete = true; break; }
             e = line_end(p, end);
             if (e == end && !final_chunk) { p = end; break; }
-            bases += rstrip_len(p, e);
+            bases += fastq ? rstrip_len(p, e) : fasta_line_bases(p, e);
             seq_end = e;
             p = e < end ? e + 1 : end;
         }
@@ -352,8 +374,8 @@ int qcb_pack_windows(const char *buf, const qcb_fastx_record *recs, int64_t n, i
                 memcpy(h, s, (size_t)k);
                 memcpy(t, e - k, (size_t)k);
             } else {                                               // wrapped record: line by line
-                copy_bases(h, s, e, 0, k);
-                copy_bases(t, s, e, r.seq_len - k, r.seq_len);
+                copy_bases(h, s, e, 0, k, r.qual_off < 0);
+                copy_bases(t, s, e, r.seq_len - k, r.seq_len, r.qual_off < 0);
             }
             wlen[i] = k;
             read_len[i] = r.seq_len;
@@ -420,7 +442,7 @@ int qcb_format_records(const char *buf, const qcb_fastx_record *recs, const qcb_
             }
             if (!blank) *o++ = ' ';
             *o++ = '\n';
-            o = put_span(o, buf + r.seq_off, r.seq_span, r.seq_len, a, b);
+            o = put_span(o, buf + r.seq_off, r.seq_span, r.seq_len, a, b, r.qual_off < 0);
             *o++ = '\n';
             if (fastq) {
                 *o++ = '+'; *o++ = '\n';
@@ -518,7 +540,7 @@ int qcb_format_stream(const char *buf, const qcb_fastx_record *recs, const qcb_r
             const int64_t l0 = label_off[label[i]], l1 = label_off[label[i] + 1];
             memcpy(o, labels + l0, (size_t)(l1 - l0)); o += l1 - l0;
             *o++ = '\n';
-            o = put_span(o, buf + r.seq_off, r.seq_span, r.seq_len, c.a, c.b);
+            o = put_span(o, buf + r.seq_off, r.seq_span, r.seq_len, c.a, c.b, r.qual_off < 0);
             *o++ = '\n';
             if (fastq) {
                 *o++ = '+'; *o++ = '\n';

@@ -218,7 +218,35 @@ def _batch_kits(vote, kit_of_layout, n_kits, batch_size):
     return kits
 
 
-def _score_chunk(scanner, plan, packed, batch_size, nobatch):
+def _read_bytes(chunk, rec):
+    """The record's sequence as Bio's parsers return it (line pieces joined; FASTA: interior blanks removed)."""
+    off, span = int(rec["seq_off"]), int(rec["seq_span"])
+    raw = chunk.data[off:off + span].tobytes()
+    if span != int(rec["seq_len"]):
+        raw = b"".join(line.rstrip() for line in raw.split(b"\n"))
+        if int(rec["qual_off"]) < 0:
+            raw = raw.replace(b" ", b"").replace(b"\r", b"")
+    return raw
+
+
+def _middle_scan_chunk(scanner, chunk, results, qcat_config):
+    """--detect-middle on the records of one chunk (scanner_base.py:593-595, after the two-end decision and before the
+    per-batch barcode filter): reads whose body read[W:-W] still holds an adapter of the detected kit become empty
+    results with exit_status 997; trims are kept."""
+    W = int(qcat_config.max_align_length)
+    tables_layouts = scanner._plan_for(qcat_config).tables.layouts
+    by_kit = {}
+    for i in np.nonzero(results["layout"] >= 0)[0].tolist():
+        by_kit.setdefault(tables_layouts[int(results["layout"][i])].kit, []).append(i)
+    for kit_name, indices in by_kit.items():
+        bodies = [_read_bytes(chunk, chunk.recs[i])[W:-W] for i in indices]
+        found = scanner._middle_found(kit_name, bodies, qcat_config)
+        for i, hit in zip(indices, found):
+            if hit:
+                results[i] = (-1, -1, 0.0, 0, results["trim5p"][i], results["trim3p"][i], 997)
+
+
+def _score_chunk(scanner, plan, packed, batch_size, nobatch, chunk=None, qcat_config=None):
     """qcb_result records of one chunk, batch semantics of the CLI loop (cli.py:500-513)."""
     win5, tail3, wlen, read_len = packed
     tables = plan.tables
@@ -242,6 +270,10 @@ def _score_chunk(scanner, plan, packed, batch_size, nobatch):
             plan.detect(win5[lo:hi], tail3[lo:hi], wlen[lo:hi], read_len[lo:hi], tables.kit_subset(kit_names[kits[b]]),
                         out=results[lo:hi])
             b = e + 1
+    if getattr(scanner, "scan_middle_adapter", False):
+        if chunk is None or qcat_config is None:
+            raise ValueError("--detect-middle needs the chunk's records (the read bodies are scanned)")
+        _middle_scan_chunk(scanner, chunk, results, qcat_config)
     if getattr(scanner, "enable_filter_barcodes", False) and not nobatch:
         _filter_barcodes(tables, results, batch_size)
     return results
@@ -476,7 +508,7 @@ def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min
                 chunk.release()
                 continue
             try:
-                results = _score_chunk(scanner, plan, packed, batch_size, nobatch)
+                results = _score_chunk(scanner, plan, packed, batch_size, nobatch, chunk, qcat_config)
             except BaseException as exc:                       # noqa: BLE001
                 failure.append(exc)
                 chunk.release()

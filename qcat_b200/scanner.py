@@ -161,51 +161,61 @@ class GpuScannerMixin(object):
         win5, tail3, wlen, read_len = packed
         return plan.detect(win5, tail3, wlen, read_len, self._subset_for(plan, kits))
 
-    def _apply_middle_scan(self, read_sequences, results, qcat_config):
-        """--detect-middle (scanner_base.py:479-519, :593-595): reads whose body still holds an adapter -> 997.
+    def _middle_found(self, kit_name, bodies, qcat_config):
+        """scan_middle's answer (scanner_base.py:479-519) for many read bodies (read[W:-W], str or bytes) of one detected
+        kit: True where the body or its reverse complement scans with barcode_score >= 50.
 
-        The reference scans read[W:-W] and, if that scores < 50, its reverse complement, one read at a time; only the
-        boolean is used, so here both windows of every read that has an adapter go to the device together, grouped by
-        detected kit and by length (window buffers of one call are bounded to ~256 MB)."""
+        The reference scans one read at a time and the reverse complement only when the forward scan fails; only the
+        boolean is used, so here both windows of every body go to the device together, sorted by length (window
+        buffers of one call are bounded to ~256 MB)."""
+        detected = self.get_adapters(kit_name)
+        if not detected:
+            raise IndexError("list index out of range")      # bc_adapter_templates[-1] in the reference's scan()
+        try:
+            plan = self._plan_for(qcat_config)
+            subset = self._subset_for(plan, detected)
+        except KeyError:
+            plan = self._plan_for(qcat_config, layouts=detected)
+            subset = list(range(len(detected)))
+        order = sorted(range(len(bodies)), key=lambda j: len(bodies[j]))
+        found_all = [False] * len(bodies)
+        start = 0
+        while start < len(order):
+            stop, longest = start, 16
+            while stop < len(order):
+                longest_next = max(longest, len(bodies[order[stop]]))
+                if stop > start and 2 * (stop + 1 - start) * longest_next > (256 << 20):
+                    break
+                longest = longest_next
+                stop += 1
+            windows = []
+            for j in order[start:stop]:
+                body = bodies[j]
+                windows.append(body)
+                windows.append(body.translate(_COMP_TABLE)[::-1] if isinstance(body, bytes) else revcomp(body))
+            recs = plan.scan_windows(windows, subset)
+            found = ~(recs["barcode_score"] < 50.0)
+            for k, j in enumerate(order[start:stop]):
+                found_all[j] = bool(found[2 * k] or found[2 * k + 1])
+            start = stop
+        return found_all
+
+    def _apply_middle_scan(self, read_sequences, results, qcat_config):
+        """--detect-middle (scanner_base.py:593-595): reads whose body still holds an adapter of the detected kit become
+        empty results with exit_status 997 (trims are kept)."""
         W = qcat_config.max_align_length
         by_kit = {}
         for i, result in enumerate(results):
             if result["adapter"]:
                 by_kit.setdefault(result["adapter"].kit, []).append(i)
         for kit_name, indices in by_kit.items():
-            detected = self.get_adapters(kit_name)
-            if not detected:
-                raise IndexError("list index out of range")      # bc_adapter_templates[-1] in the reference's scan()
-            try:
-                plan = self._plan_for(qcat_config)
-                subset = self._subset_for(plan, detected)
-            except KeyError:
-                plan = self._plan_for(qcat_config, layouts=detected)
-                subset = list(range(len(detected)))
-            indices.sort(key=lambda i: len(read_sequences[i] or ""))
-            start = 0
-            while start < len(indices):
-                stop, longest = start, 16
-                while stop < len(indices):
-                    longest_next = max(longest, len(read_sequences[indices[stop]] or ""))
-                    if stop > start and 2 * (stop + 1 - start) * longest_next > (256 << 20):
-                        break
-                    longest = longest_next
-                    stop += 1
-                windows = []
-                for i in indices[start:stop]:
-                    body = (read_sequences[i] or "")[W:-W]
-                    windows.append(body)
-                    windows.append(revcomp(body))
-                recs = plan.scan_windows(windows, subset)
-                found = ~(recs["barcode_score"] < 50.0)
-                for j, i in enumerate(indices[start:stop]):
-                    if found[2 * j] or found[2 * j + 1]:
-                        trims = results[i]["trim5p"], results[i]["trim3p"]
-                        results[i] = empty_return_dict()
-                        results[i]["exit_status"] = 997
-                        results[i]["trim5p"], results[i]["trim3p"] = trims
-                start = stop
+            found = self._middle_found(kit_name, [(read_sequences[i] or "")[W:-W] for i in indices], qcat_config)
+            for i, hit in zip(indices, found):
+                if hit:
+                    trims = results[i]["trim5p"], results[i]["trim3p"]
+                    results[i] = empty_return_dict()
+                    results[i]["exit_status"] = 997
+                    results[i]["trim5p"], results[i]["trim3p"] = trims
 
     def scan_middle(self, sequence, kit_name, qcat_config):
         detected = self.get_adapters(kit_name)

@@ -23,7 +23,7 @@ def oracle_lib():
     global _oracle
     if _oracle is None:
         lib = ctypes.CDLL(oracle_build.build())
-        for name in ("qo_sg", "qo_detect", "qo_kit_vote", "qo_find_best_adapter_template"):
+        for name in ("qo_sg", "qo_detect", "qo_scan", "qo_kit_vote", "qo_find_best_adapter_template"):
             getattr(lib, name).restype = None
         lib.qo_count_cells.restype = ctypes.c_int64
         _oracle = lib
@@ -48,6 +48,25 @@ def oracle_detect(tables, win5, tail3, wlen, read_len, subset=None, threads=None
     lib.qo_detect(ctypes.byref(st), _vp(win5), _vp(tail3), ctypes.c_int(win5.shape[1]), _vp(wlen), _vp(read_len),
                   ctypes.c_int64(n), _vp(sub), ctypes.c_int(0 if sub is None else sub.size), _vp(out),
                   ctypes.c_int(threads or os.cpu_count() or 1))
+    return out
+
+
+def oracle_scan(tables, windows, subset=None, threads=None):
+    """qo_scan on a list of already oriented windows (str / bytes, any length) -> structured array."""
+    lib = oracle_lib()
+    st, keep = _ffi.tables_struct(tables)
+    raw = [w if isinstance(w, bytes) else (w or "").encode("latin-1", "replace") for w in windows]
+    n = len(raw)
+    stride = max([len(r) for r in raw] + [1])
+    buf = np.zeros((n, stride), dtype=np.uint8)
+    wlen = np.zeros(n, dtype=np.int32)
+    for i, r in enumerate(raw):
+        wlen[i] = len(r)
+        buf[i, :len(r)] = np.frombuffer(r, dtype=np.uint8)
+    out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+    sub = None if subset is None else np.ascontiguousarray(subset, dtype=np.int32)
+    lib.qo_scan(ctypes.byref(st), _vp(buf), ctypes.c_int64(stride), _vp(wlen), ctypes.c_int64(n), _vp(sub),
+                ctypes.c_int(0 if sub is None else sub.size), _vp(out), ctypes.c_int(threads or os.cpu_count() or 1))
     return out
 
 
@@ -143,3 +162,7 @@ class OraclePlan(object):
 
     def kit_vote(self, win5, tail3, wlen):
         return oracle_kit_vote(self.tables, win5, tail3, wlen)
+
+    def scan_windows(self, windows, subset=None):
+        self.calls += 1
+        return oracle_scan(self.tables, windows, subset)

@@ -118,3 +118,28 @@ def test_fasta(recs, wrap, threads):
     assert outcome[0] == "ok"
     got = np.frombuffer(outcome[1], dtype=fastx._ffi.RECORD_DTYPE)
     check_against_model(buf, [(t, s, "") for t, s in recs], got)
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(recs=st.lists(st.tuples(TITLE.filter(lambda t: ">" not in t),
+                               st.text(alphabet="ACGTN \r", min_size=0, max_size=80)), min_size=1, max_size=20),
+       wrap=st.integers(min_value=5, max_value=60), threads=st.integers(min_value=2, max_value=9))
+def test_fasta_interior_blanks(recs, wrap, threads):
+    """Blanks and carriage returns INSIDE FASTA sequence lines are not bases: Bio's SimpleFastaParser (what cli.py:235-306
+    iterates with) joins line.rstrip() pieces and then removes every ' ' and '\\r'."""
+    text = "".join(">%s\n%s" % (t, "".join(s[i:i + wrap] + "\n" for i in range(0, len(s), wrap)) or "\n") for t, s in recs)
+    buf = text.encode("latin-1")
+    outcome = same_outcome(buf, True, -threads)
+    assert outcome[0] == "ok"
+    got = np.frombuffer(outcome[1], dtype=fastx._ffi.RECORD_DTYPE)
+    assert len(got) == len(recs)
+    want = []
+    for _, s in recs:
+        lines = [s[i:i + wrap] for i in range(0, len(s), wrap)]
+        want.append("".join(l.rstrip() for l in lines).replace(" ", "").replace("\r", ""))
+    pack = fastx.pack_windows(buf, got, 30, threads=2)
+    for i, seq in enumerate(want):
+        k = min(len(seq), 30)
+        assert int(got[i]["seq_len"]) == len(seq)
+        assert pack[2][i] == k and pack[3][i] == len(seq)
+        assert pack[0][i, :k].tobytes().decode() == seq[:k] and pack[1][i, :k].tobytes().decode() == seq[len(seq) - k:]

@@ -140,3 +140,34 @@ def test_demux_file_propagates_errors(tmp_path):
         fastx.demux_file(str(good), sc, chunk_bytes=100000)
     with pytest.raises(IOError):
         fastx.demux_file(str(tmp_path / "missing.fastq"), sc)
+
+
+@pytest.mark.parametrize("kit,filter_barcodes", [("PBC096", False), (None, True)])
+def test_demux_file_detect_middle_matches_reference_cli(tmp_path, kit, filter_barcodes):
+    """`--detect-middle` through demux_file (scanner_base.py:479-519, :593-595): chimeric reads become `none` (exit
+    status 997) exactly where the reference CLI says so -- before the per-batch barcode filter, wrapped FASTA included."""
+    refloader.load()
+    from qcat import scanner as ref_scanner
+    from qcat_b200 import fastx, synth
+    layouts = ref_scanner.factory(kit=kit or "RBK004").layouts
+    plain = synth.windows_to_reads(synth.generate(layouts, 160, seed=37, mean_len=900.0, sub=0.02, dele=0.01, ins=0.01))
+    reads = [plain[i] + plain[i + 1] if i % 3 else plain[i] for i in range(0, len(plain), 2)]
+    reads += ["", "ACGT" * 60, plain[0][:310], plain[1][:299]]
+    path = tmp_path / "reads.fasta"
+    with open(path, "w") as fh:
+        for i, r in enumerate(reads):
+            fh.write(">read%d\n" % i + ("".join(r[j:j + 70] + "\n" for j in range(0, len(r), 70)) or "\n"))
+    argv = ["-f", str(path), "--detect-middle"] + (["-k", kit] if kit else []) + (["--filter-barcodes"] if filter_barcodes else [])
+    tsv_cpu = _run_cli(argv + ["--tsv", "-b", str(tmp_path / "cpu")])
+    files_cpu = {name: open(tmp_path / "cpu" / name).read() for name in sorted(os.listdir(tmp_path / "cpu"))}
+    sc = _oracle_scanner("epi2me", kit, enable_filter_barcodes=filter_barcodes, scan_middle_adapter=True)
+    tsv = io.StringIO()
+    summary = fastx.demux_file(str(path), sc, tsv=tsv, out_dir=str(tmp_path / "native"), chunk_bytes=60000,
+                               min_read_length=100)              # the CLI's default
+    files_native = {name: open(tmp_path / "native" / name).read() for name in sorted(os.listdir(tmp_path / "native"))}
+    assert tsv.getvalue() == tsv_cpu
+    assert files_native == files_cpu
+    assert int((summary["records"]["exit_status"] == 997).sum()) >= 5
+    # without the flag the same reads stay classified: the scan is what made the difference
+    plain_sc = _oracle_scanner("epi2me", kit, enable_filter_barcodes=filter_barcodes)
+    assert int((fastx.demux_file(str(path), plain_sc)["records"]["exit_status"] == 997).sum()) == 0
