@@ -7,8 +7,14 @@
 A step = one pass of the hot path (window orientation -> adapter DP -> template choice -> barcode DP -> two-end
 decision) over one batch of synthetic reads per GPU.  `value` is measured with the batch resident in HBM (CUDA
 events on the launching stream), `e2e` through the host-buffer C-ABI call (pinned host memory in, records out).
-Reads are sharded across ranks (weak scaling, no data-path collective); the single NCCL all-gather of the
-per-barcode counts happens once, at the end of the timed region.  One JSON line on stdout (rank 0).
+Reads are sharded round-robin across ranks (weak scaling: global read i of a step belongs to rank i % N, every rank
+draws its own shard; no data-path collective); the single NCCL all-gather of the per-barcode counts happens once, at
+the end of the timed region.  One JSON line on stdout (rank 0).
+
+Besides the headline workload the line carries, under `workloads`, the same measurements for the other BASELINE
+configs (configs[1] NBD104, configs[2] on the synthetic EXP-NBD196 kit, configs[3] dual, configs[4] mixed read lengths
+with --trim offsets checked, and the CLI's default auto-kit mode), a fixed-size strong-scaling pass (`strong_scaling`,
+10 M reads split over the ranks) and, when N > 1, an N-GPU == 1-GPU parity check on one round-robin sharded dataset.
 """
 import argparse
 import json
@@ -37,18 +43,34 @@ def emit_result(line):
         os.write(_RESULT_FD, data)
 
 
+def log(msg):
+    sys.stderr.write("[bench] %s\n" % msg)
+    sys.stderr.flush()
+
+
 ALGORITHMIC_BYTES_PER_READ = 336     # 2 x 150 B windows + 4 B length in, one 32 B record out
-CONFIG_INDEX = 2                     # BASELINE.json configs[2]: 96 barcodes, 1 -> 8 GPUs
-KIT = "PBC096"                       # the reference's 96-barcode EPI2ME kit (NBD196 does not exist in qcat 1.1.0)
-# Other BASELINE configs, selectable with --workload (parity-test cases, not the headline bench line):
+METRIC = "reads/s demuxed (96-barcode EPI2ME, 150bp windows)"
+NBD196_FOLDER = os.path.join(ROOT, "qcat_b200", "resources", "nbd196")
+MIXED_LENGTHS = {"min_len": 500, "max_len": 50000, "length_model": "loguniform"}
+
+# BASELINE.json configs.  configs[2] is the headline (its metric is the bench line's `value`); the others are measured
+# after it and reported under `workloads`.  kit None = the scanner's default kit selection (dual: the DUAL kit; epi2me:
+# every auto-detect layout, i.e. the CLI's `-k auto`).
 WORKLOADS = {
-    "configs[1]": ("NBD103/NBD104", "epi2me", "12-barcode NBD104 kit"),
-    "configs[2]": ("PBC096", "epi2me", "96-barcode PBC096 kit"),
-    "configs[2]-nbd196": ("NBD196", "epi2me", "synthetic 96-barcode EXP-NBD196 kit (NBD104 flanks + revcomp of the PBC096 "
-                                             "barcodes, tools/make_nbd196.py)"),
-    "configs[3]": (None, "dual", "dual barcoding, 24 x 96 pairs (DUAL kit)"),
-    "configs[4]": ("PBC096", "epi2me", "96-barcode PBC096 kit, --trim (trim offsets are part of every record)"),
+    "configs[1]": {"index": 1, "kit": "NBD103/NBD104", "mode": "epi2me", "what": "12-barcode NBD104 kit"},
+    "configs[2]": {"index": 2, "kit": "PBC096", "mode": "epi2me", "what": "96-barcode PBC096 kit"},
+    "configs[2]-nbd196": {"index": 2, "kit": "NBD196", "mode": "epi2me", "kit_folder": NBD196_FOLDER,
+                          "what": "synthetic 96-barcode EXP-NBD196 kit (NBD104 flanks + revcomp of the PBC096 barcodes, "
+                                  "tools/make_nbd196.py)"},
+    "configs[3]": {"index": 3, "kit": None, "mode": "dual", "what": "dual barcoding, 24 x 96 pairs (DUAL kit)"},
+    "configs[4]": {"index": 4, "kit": "PBC096", "mode": "epi2me", "gen": MIXED_LENGTHS, "trim_check": True,
+                   "what": "96-barcode PBC096 kit, --trim, read lengths log-uniform in 500 bp - 50 kb (trim offsets "
+                           "are part of every record and are checked)"},
+    "auto-kit": {"index": 2, "kit": None, "mode": "epi2me", "auto": True, "source_kit": "PBC096",
+                 "what": "the CLI default `-k auto`: 12 auto-detect layouts, per-4000-read kit vote on the device, then "
+                         "the voted kit's layouts (PBC096 reads)"},
 }
+EXTRA_WORKLOADS = ("configs[1]", "configs[2]-nbd196", "configs[3]", "configs[4]", "auto-kit")
 
 
 def parse_args():
@@ -58,39 +80,41 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads-per-step", type=int, default=1000000, help="reads per GPU per step")
-    ap.add_argument("--unique-reads", type=int, default=262144, help="distinct synthetic reads generated (tiled up)")
+    ap.add_argument("--unique-reads", type=int, default=0, help="distinct synthetic reads generated per GPU (0 = all)")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="reads timed on the CPU oracle (cpu_baseline)")
-    ap.add_argument("--workload", default="configs[2]", choices=sorted(WORKLOADS))
-    ap.add_argument("--kit", default=None)
-    ap.add_argument("--mode", default=None, choices=["epi2me", "dual"])
+    ap.add_argument("--workload", default="configs[2]", choices=sorted(WORKLOADS), help="the headline workload")
+    ap.add_argument("--extra-workloads", default=",".join(EXTRA_WORKLOADS),
+                    help="comma-separated workloads measured after the headline ('' = none)")
+    ap.add_argument("--extra-steps", type=int, default=3)
+    ap.add_argument("--strong-reads", type=int, default=10000000, help="fixed job size of the strong-scaling pass (0 = skip)")
     ap.add_argument("--force-generic", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     return ap.parse_args()
 
 
-NBD196_FOLDER = os.path.join(ROOT, "qcat_b200", "resources", "nbd196")
-
-
-def make_scanner_tables(kit, mode):
+def make_scanner_tables(spec):
     from qcat_b200 import config, scanner
     from qcat_b200.tables import Tables
-    cls = scanner.BarcodeScannerDual if mode == "dual" else scanner.BarcodeScannerEPI2ME
+    cls = scanner.BarcodeScannerDual if spec["mode"] == "dual" else scanner.BarcodeScannerEPI2ME
     # NBD196 is not a qcat kit: it is loaded from its own kit folder, like any custom kit (adapters.py:138-162)
-    sc = cls(kit=kit, kit_folder=NBD196_FOLDER if kit == "NBD196" else None)
-    return sc, Tables(sc.layouts, config.qcatConfig(), mode, sc.min_quality)
+    sc = cls(kit=spec["kit"], kit_folder=spec.get("kit_folder"))
+    return sc, Tables(sc.layouts, config.qcatConfig(), spec["mode"], sc.min_quality)
 
 
-def synth_batch(sc, n, unique, seed):
+def synth_batch(spec, sc, n, unique, seed):
+    """n reads for one rank and step: `unique` distinct reads (all of them unless --unique-reads says otherwise)."""
     from qcat_b200 import scanner, synth
     foreign = scanner.BarcodeScannerEPI2ME(kit="RBK001").layouts
-    u = min(n, unique)
-    d = synth.generate(sc.layouts, u, seed=seed, foreign_layouts=foreign)
-    reps = (n + u - 1) // u
+    layouts = sc.layouts
+    if spec.get("source_kit"):                         # auto-kit workload: reads of one kit, scanner knows them all
+        layouts = scanner.BarcodeScannerEPI2ME(kit=spec["source_kit"]).layouts
+    u = n if unique <= 0 else min(n, unique)
+    d = synth.generate_parallel(layouts, u, seed=seed, foreign_layouts=foreign, **spec.get("gen", {}))
     out = {}
     for k in ("win5", "tail3", "wlen", "read_len"):
-        out[k] = np.ascontiguousarray(np.concatenate([d[k]] * reps, axis=0)[:n])
-    return out
+        out[k] = d[k] if u == n else np.ascontiguousarray(np.concatenate([d[k]] * ((n + u - 1) // u), axis=0)[:n])
+    return out, u
 
 
 class ClockSampler(object):
@@ -146,19 +170,25 @@ class ClockSampler(object):
                 "samples": len(sm)}
 
 
-def cpu_oracle_rate(tables, batch, sample, threads):
-    """Reads/s of the CPU oracle (C port of the reference path, OpenMP over reads) on the first `sample` reads."""
+def oracle_records(spec, sc, tables, batch, threads=None):
     from tests import helpers
+    if spec.get("auto"):
+        return helpers.oracle_detect_auto(tables, batch["win5"], batch["tail3"], batch["wlen"], batch["read_len"], 4000, threads=threads)
+    return helpers.oracle_detect(tables, batch["win5"], batch["tail3"], batch["wlen"], batch["read_len"], threads=threads)
+
+
+def cpu_oracle_rate(spec, sc, tables, batch, sample, threads):
+    """Reads/s of the CPU oracle (C port of the reference path, OpenMP over reads) on the first `sample` reads."""
     n = min(sample, len(batch["wlen"]))
     sub = {k: batch[k][:n] for k in batch}
-    helpers.oracle_detect(tables, sub["win5"][:256], sub["tail3"][:256], sub["wlen"][:256], sub["read_len"][:256], threads=threads)
+    oracle_records(spec, sc, tables, {k: sub[k][:256] for k in sub}, threads)
     t0 = time.perf_counter()
-    res = helpers.oracle_detect(tables, sub["win5"], sub["tail3"], sub["wlen"], sub["read_len"], threads=threads)
+    oracle_records(spec, sc, tables, sub, threads)
     dt = time.perf_counter() - t0
-    return n / dt, n, res
+    return n / dt, n
 
 
-def reference_python_rate(args, batch, n_reads=1500):
+def reference_python_rate(spec, batch, n_reads=1500):
     """Reads/s of the UNMODIFIED reference Python (qcat.scanner.factory(...).detect_barcode_batch in CLI batches of 4000,
     one process -- the reference has no other mode) over the parasail stand-in of oracle/refshim, on the first n_reads
     reads of the batch.  None when the reference package did not travel to this box.  Never raises."""
@@ -172,8 +202,8 @@ def reference_python_rate(args, batch, n_reads=1500):
         from qcat import config as ref_config
         from qcat import scanner as ref_scanner
         from qcat_b200 import synth
-        kw = {"kit_folder": NBD196_FOLDER} if args.kit == "NBD196" else {}
-        sc = ref_scanner.factory(mode=args.mode, kit=args.kit, **kw)
+        kw = {"kit_folder": spec["kit_folder"]} if spec.get("kit_folder") else {}
+        sc = ref_scanner.factory(mode=spec["mode"], kit=spec["kit"], **kw)
         n = min(n_reads, len(batch["wlen"]))
         reads = synth.windows_to_reads({k: batch[k][:n] for k in batch})
         cfg = ref_config.qcatConfig()
@@ -188,139 +218,225 @@ def reference_python_rate(args, batch, n_reads=1500):
         return {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
 
 
+def workload_config(name, spec, reads_per_step):
+    """`config` of the JSON line: identical for both arms (the reference arm's bounded sample is in its cpu_baseline)."""
+    return {"workload": "BASELINE %s: %s, %s mode, 150 nt windows, synthetic reads mean 8 kb "
+                        "(8%% sub / 6%% del / 5%% ins on adapters, 10%% unbarcoded)" % (name, spec["what"], spec["mode"]),
+            "kit": spec["kit"] or ("DUAL" if spec["mode"] == "dual" else "auto"), "mode": spec["mode"],
+            "reads_per_gpu_per_step": reads_per_step,
+            "window": 150, "sharding": "reads sharded round-robin across ranks, one all-gather of per-barcode counts at the end",
+            "l2": "inputs larger than L2 (%.0f MB per step per GPU)" % (reads_per_step * 332 / 1e6)}
+
+
 def run_reference(args):
+    """The reference's CPU implementation of the path (C oracle port of it, all host threads) on a bounded sample of
+    the headline workload.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sc, tables = make_scanner_tables(args.kit, args.mode)
+    name = args.workload
+    spec = WORKLOADS[name]
+    sc, tables = make_scanner_tables(spec)
     threads = os.cpu_count() or 1
-    batch = synth_batch(sc, args.cpu_sample, args.unique_reads, seed=20261017 + CONFIG_INDEX)
-    from tests import helpers
+    sample = args.cpu_sample
+    # the generator draws chunks of 65536 reads: whole chunks, so that these ARE the first reads of rank 0's step batch
+    batch, _ = synth_batch(spec, sc, (sample + 65535) // 65536 * 65536, 0, seed=[20261017, spec["index"], 0])
+    batch = {k: v[:sample] for k, v in batch.items()}
     for _ in range(max(args.warmup, 1)):
-        helpers.oracle_detect(tables, batch["win5"][:512], batch["tail3"][:512], batch["wlen"][:512], batch["read_len"][:512],
-                              threads=threads)
+        oracle_records(spec, sc, tables, {k: batch[k][:512] for k in batch}, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        helpers.oracle_detect(tables, batch["win5"], batch["tail3"], batch["wlen"], batch["read_len"], threads=threads)
+        oracle_records(spec, sc, tables, batch, threads)
     dt = time.perf_counter() - t0
-    value = args.steps * args.cpu_sample / dt
-    sample = "%d synthetic %s reads per step (bounded sample of the 10M-read config), %d steps" % (args.cpu_sample, args.kit, args.steps)
-    line = {"impl": "reference", "metric": "reads/s demuxed (96-barcode EPI2ME, 150bp windows)", "value": value, "unit": "reads/s",
+    value = args.steps * sample / dt
+    text = ("each step = the first %d reads of the %d-read step batch (same generator and seed as the GPU arm's rank 0), "
+            "%d steps, C oracle port, OpenMP over reads" % (sample, args.reads_per_step, args.steps))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": workload_config(args, args.cpu_sample),
-            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": sample,
+            "config": workload_config(name, spec, args.reads_per_step),
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": text,
                              "note": "reference = pure Python over parasail (not installable offline); this is the C oracle "
                                      "port of that path, scalar int32 affine DP, OpenMP over reads",
-                             "reference_python": reference_python_rate(args, batch)},
+                             "reference_python": reference_python_rate(spec, batch)},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_result(line)
     return 0
 
 
-def workload_config(args, reads_per_step):
-    return {"workload": "BASELINE %s: %s, %s mode, 150 nt windows, synthetic reads mean 8 kb "
-                        "(8%% sub / 6%% del / 5%% ins on adapters, 10%% unbarcoded)" % (args.workload, WORKLOADS[args.workload][2], args.mode),
-            "kit": args.kit, "mode": args.mode, "reads_per_gpu_per_step": reads_per_step,
-            "window": 150, "sharding": "reads sharded across ranks, one all-gather of per-barcode counts at the end",
-            "l2": "inputs larger than L2 (%.0f MB per step per GPU)" % (reads_per_step * 332 / 1e6)}
+KERNEL_NAMES = {"orient": "k_orient_codes", "adapter": "k_adapter_fast", "select": "k_select", "barcode": "k_barcode_fast",
+                "decide": "k_finalize", "context": "k_context"}
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from qcat_b200 import _ffi, engine
+class Workload(object):
+    """One BASELINE config on this rank: scanner tables, the rank's synthetic shard, device buffers, plan."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the CUDA path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
+    def __init__(self, name, args, rank, world):
+        self.name, self.spec, self.args = name, WORKLOADS[name], args
+        self.rank, self.world = rank, world
+        self.sc, self.tables = make_scanner_tables(self.spec)
+        self.n = args.reads_per_step
+        t0 = time.perf_counter()
+        # global read i of a step belongs to rank i % world (round-robin): rank r draws shard r
+        self.batch, self.unique = synth_batch(self.spec, self.sc, self.n, args.unique_reads,
+                                              seed=[20261017, self.spec["index"], rank])
+        self.gen_s = time.perf_counter() - t0
+        self.stride = int(self.batch["win5"].shape[1])
+        self.names = [l.kit for l in self.sc.layouts]
+        self.kit_of_layout = None
 
-    sc, tables = make_scanner_tables(args.kit, args.mode)
-    plan = engine.DevicePlan(tables, device=local_rank)
-    plan.set_force_generic(args.force_generic)
-    n = args.reads_per_step
-    batch = synth_batch(sc, n, args.unique_reads, seed=20261017 + CONFIG_INDEX + 1000 * rank)
-    stride = batch["win5"].shape[1]
+    def to_device(self, torch, dev, local_rank):
+        from qcat_b200 import engine
+        self.torch, self.dev = torch, dev
+        self.plan = engine.DevicePlan(self.tables, device=local_rank)
+        self.plan.set_force_generic(self.args.force_generic)
+        b = self.batch
+        self.d_win5 = torch.from_numpy(b["win5"]).to(dev)
+        self.d_tail3 = torch.from_numpy(b["tail3"]).to(dev)
+        self.d_wlen = torch.from_numpy(b["wlen"]).to(dev)
+        self.d_rlen = torch.from_numpy(b["read_len"]).to(dev)
+        self.d_out = torch.zeros(self.n * 32, dtype=torch.uint8, device=dev)
+        self.base, self.n_bins = self.plan.histogram_layout()
+        self.d_counts = torch.zeros(self.n_bins, dtype=torch.int64, device=dev)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        if self.spec.get("auto"):
+            kit_names = list(dict.fromkeys(self.names))
+            self.kit_of_layout = np.array([kit_names.index(k) for k in self.names], dtype=np.int32)
 
-    d_win5 = torch.from_numpy(batch["win5"]).to(dev)
-    d_tail3 = torch.from_numpy(batch["tail3"]).to(dev)
-    d_wlen = torch.from_numpy(batch["wlen"]).to(dev)
-    d_rlen = torch.from_numpy(batch["read_len"]).to(dev)
-    d_out = torch.zeros(n * 32, dtype=torch.uint8, device=dev)
-    base, n_bins = plan.histogram_layout()
-    d_counts = torch.zeros(n_bins, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    def free_device(self):
+        for k in ("d_win5", "d_tail3", "d_wlen", "d_rlen", "d_out", "d_counts"):
+            setattr(self, k, None)
+        self.plan.close()
+        self.torch.cuda.empty_cache()
 
-    def step():
-        plan.detect_device(d_win5.data_ptr(), d_tail3.data_ptr(), stride, d_wlen.data_ptr(), d_rlen.data_ptr(), n,
-                           d_out.data_ptr(), stream=stream)
-        plan.histogram_device(d_out.data_ptr(), n, base, d_counts.data_ptr(), n_bins, stream=stream)
+    def step(self, n=None, d_in=None, d_out=None):
+        n = self.n if n is None else n
+        win5, tail3, wlen, rlen = d_in or (self.d_win5, self.d_tail3, self.d_wlen, self.d_rlen)
+        out = self.d_out if d_out is None else d_out
+        if self.spec.get("auto"):
+            self.plan.detect_auto_device(win5.data_ptr(), tail3.data_ptr(), self.stride, wlen.data_ptr(), rlen.data_ptr(), n,
+                                         self.kit_of_layout, 4000, out.data_ptr(), stream=self.stream)
+        else:
+            self.plan.detect_device(win5.data_ptr(), tail3.data_ptr(), self.stride, wlen.data_ptr(), rlen.data_ptr(), n,
+                                    out.data_ptr(), stream=self.stream)
+        self.plan.histogram_device(out.data_ptr(), n, self.base, self.d_counts.data_ptr(), self.n_bins, stream=self.stream)
 
-    def barrier():
-        if world > 1:
+    def detect_host(self, hv, out_view):
+        if self.spec.get("auto"):
+            return self.plan.detect_auto(hv["win5"], hv["tail3"], hv["wlen"], hv["read_len"], self.kit_of_layout, 4000, out=out_view)
+        return self.plan.detect(hv["win5"], hv["tail3"], hv["wlen"], hv["read_len"], out=out_view)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
             dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, steps, warmup, sampler=None):
+        """(elapsed ms of `steps` steps + the count all-gather, max over ranks; gathered total counts; kernel launches)."""
+        torch = self.torch
+        for _ in range(max(warmup, 3)):
+            self.step()
+        if self.world > 1:                                     # warm the communicator outside the timed region
+            import torch.distributed as dist
+            dist.all_gather([torch.zeros_like(self.d_counts) for _ in range(self.world)], self.d_counts)
+        self.barrier()
+        self.d_counts.zero_()
+        launches0 = self.plan.info()["kernel_launches"]
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.3)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.step()
+        if self.world > 1:
+            import torch.distributed as dist
+            gathered = [torch.zeros_like(self.d_counts) for _ in range(self.world)]
+            dist.all_gather(gathered, self.d_counts)          # the path's only collective: per-barcode counts, once
+            total_counts = torch.stack(gathered).sum(0)
+        else:
+            total_counts = self.d_counts
+        e1.record()
+        self.barrier()
+        elapsed_ms = self.max_over_ranks(e0.elapsed_time(e1))
+        launches = self.plan.info()["kernel_launches"] - launches0
+        assert int(total_counts.sum().item()) == self.world * self.n * steps, "histogram does not account for every read"
+        return elapsed_ms, total_counts, int(launches)
+
+    def stage_profile(self, prof_steps=2):
+        self.plan.set_profiling(True)
+        self.plan.stage_times(reset=True)
+        for _ in range(prof_steps):
+            self.step()
+        self.torch.cuda.synchronize()
+        stages = self.plan.stage_times(reset=True)
+        self.plan.set_profiling(False)
+        return {k: (v[0] / prof_steps, max(1, v[1] // prof_steps) if v[1] else 0) for k, v in stages.items()}
+
+    def e2e(self, steps):
+        """Through the host-buffer C ABI: pinned host memory in, records out; H2D + D2H inside the timed region."""
+        from qcat_b200 import _ffi
+        torch = self.torch
+        h = {k: torch.from_numpy(self.batch[k]).pin_memory() for k in ("win5", "tail3", "wlen", "read_len")}
+        h_out = torch.zeros(self.n * 32, dtype=torch.uint8).pin_memory()
+        hv = {k: v.numpy() for k, v in h.items()}
+        out_view = h_out.numpy().view(_ffi.RESULT_DTYPE)
+        for _ in range(2):
+            self.detect_host(hv, out_view)
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.detect_host(hv, out_view)
         torch.cuda.synchronize()
+        dt = self.max_over_ranks(time.perf_counter() - t0)
+        res = {"value": self.world * self.n * steps / dt, "unit": "reads/s",
+               "h2d_bytes_per_step": int(self.n * (2 * self.stride + 4 + 8)), "d2h_bytes_per_step": int(self.n * 32),
+               "api": "qcb_detect_auto" if self.spec.get("auto") else "qcb_detect", "buffers": "pinned host"}
+        return res, out_view
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    if world > 1:                                          # warm the communicator outside the timed region
-        dist.all_gather([torch.zeros_like(d_counts) for _ in range(world)], d_counts)
-    barrier()
-    d_counts.zero_()
-    launches0 = plan.info()["kernel_launches"]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    if world > 1:
-        gathered = [torch.zeros_like(d_counts) for _ in range(world)]
-        dist.all_gather(gathered, d_counts)            # the path's only collective: per-barcode counts, once
-        total_counts = torch.stack(gathered).sum(0)
-    else:
-        total_counts = d_counts
-    e1.record()
-    barrier()
-    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(elapsed_ms.item())
-    clocks = sampler.stop() if rank == 0 else None
-    launches = plan.info()["kernel_launches"] - launches0
-    value = world * n * args.steps / (elapsed_ms * 1e-3)
-    assert int(total_counts.sum().item()) == world * n * args.steps, "histogram does not account for every read"
+    def parity_head(self, records, count=2000):
+        """Rank 0: the first `count` records against the CPU oracle (auto-kit: whole CLI batches)."""
+        from tests import helpers
+        if self.spec.get("auto"):
+            count = 4000
+        sub = {k: self.batch[k][:count] for k in self.batch}
+        want = oracle_records(self.spec, self.sc, self.tables, sub)
+        helpers.assert_records_equal(records[:count], want, "bench parity spot check (%s)" % self.name)
+        return "%d records bit-identical to the CPU oracle" % count
 
-    # ---- per-stage profile (outside the timed region): dominant kernel and its roofline -------------
-    plan.set_profiling(True)
-    plan.stage_times(reset=True)
-    prof_steps = 2
-    for _ in range(prof_steps):
-        step()
-    torch.cuda.synchronize()
-    stages = plan.stage_times(reset=True)
-    plan.set_profiling(False)
+    def trim_check(self, records):
+        """configs[4]: trim offsets of the whole batch are what `--trim` slices with (cli.py:521-526): inside the read,
+        ordered, and adapter ends inside the windows."""
+        rl = self.batch["read_len"]
+        t5, t3 = records["trim5p"].astype(np.int64), records["trim3p"].astype(np.int64)
+        assert ((0 <= t5) & (t5 <= t3) & (t3 <= rl)).all(), "trim offsets out of order"
+        assert ((t5 <= 150 + 26) & (rl - t3 <= 150 + 26)).all(), "trim offsets outside the scored windows"
+        trimmed = (t5 > 0) | (t3 < rl)
+        return {"reads_trimmed_frac": float(trimmed.mean()), "mean_bases_removed": float((rl - (t3 - t5)).mean()),
+                "read_len_min": int(rl.min()), "read_len_max": int(rl.max()), "read_len_median": float(np.median(rl))}
+
+
+def hbm_roofline(w, stages, args):
+    """`roofline` of the contract for the dominant kernel of this workload."""
     total_stage_ms = sum(v[0] for v in stages.values()) or 1.0
     dom = max(stages, key=lambda k: stages[k][0])
-    dom_ms = stages[dom][0] / prof_steps
-    dom_launches = max(1, stages[dom][1] // prof_steps)              # the step runs in chunks of <= 262144 reads
-    kernel_names = {"orient": "k_orient_codes", "adapter": "k_adapter_fast", "select": "k_select", "barcode": "k_barcode_fast",
-                    "decide": "k_finalize", "context": "k_context"}
-    traffic = None                                                    # DRAM bytes per read of that kernel, from the ncu capture
+    dom_ms, dom_launches = stages[dom][0], max(1, stages[dom][1])
+    kernel = KERNEL_NAMES.get(dom, dom)
+    traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            per_read = json.load(fh).get(kernel_names.get(dom, dom), {}).get("dram_bytes_per_read")
-            if per_read is not None and not args.force_generic:
-                traffic = per_read * n / dom_launches
+            per_read = json.load(fh).get(kernel, {}).get("dram_bytes_per_read")
+            if per_read is not None and not args.force_generic and w.name.startswith("configs[2]"):
+                traffic = per_read * w.n / dom_launches
     except (OSError, ValueError):
         pass
     peaks = {}
@@ -330,39 +446,48 @@ def run_ours(args):
     except OSError:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved_gbs = ALGORITHMIC_BYTES_PER_READ * n / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": kernel_names.get(dom, dom) if not args.force_generic else dom + " (generic)",
-                "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": traffic,
-                "launches_per_step": dom_launches, "ms_per_launch": dom_ms / dom_launches,
-                "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_READ * n / dom_launches,
-                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                "algorithmic_bytes_per_read": ALGORITHMIC_BYTES_PER_READ,
-                "kernel_ms_per_launch_set": dom_ms, "kernel_share_of_step": stages[dom][0] / total_stage_ms,
-                "stage_ms_per_step": {k: v[0] / prof_steps for k, v in stages.items()},
-                "note": "integer-DP path: HBM fraction is ~0 by construction (SURVEY F4); the binding roofline is "
-                        "compute_roofline below"}
+    achieved_gbs = ALGORITHMIC_BYTES_PER_READ * w.n / (dom_ms * 1e-3) / 1e9
+    return dom, {"bound": "hbm", "kernel": kernel if not args.force_generic else dom + " (generic)",
+                 "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                 "frac": achieved_gbs / hbm_peak, "traffic": traffic,
+                 "launches_per_step": dom_launches, "ms_per_launch": dom_ms / dom_launches,
+                 "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_READ * w.n / dom_launches,
+                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                 "algorithmic_bytes_per_read": ALGORITHMIC_BYTES_PER_READ,
+                 "kernel_ms_per_launch_set": dom_ms, "kernel_share_of_step": stages[dom][0] / total_stage_ms,
+                 "stage_ms_per_step": {k: v[0] for k, v in stages.items()},
+                 "note": "integer-DP path: HBM fraction is ~0 by construction (SURVEY F4); the binding roofline is "
+                         "compute_roofline"}
 
-    # compute roofline: DP cells per second against the measured issue rate of the packed DP cell
+
+def compute_roofline(w, step_ms, dom, dom_ms, clocks, local_rank, args):
+    """DP cells per second against the measured issue rate of the instruction pair the packed kernels run
+    (IMAD.IADD + VIMNMX3.U16x2 per two cells, qcb_microbench_cell_rate) at the SM clock sampled under load."""
+    from qcat_b200 import engine
     from tests import helpers
+    tables, batch, n = w.tables, w.batch, w.n
     ncells_sample = min(n, 20000)
     ref_cells, full = helpers.oracle_count_cells(tables, batch["win5"][:ncells_sample], batch["tail3"][:ncells_sample],
                                                  batch["wlen"][:ncells_sample])
     cells_per_read = ref_cells / ncells_sample
     cell_peak, mb_mhz = engine.microbench_cell_rate(local_rank)
-    # the micro-benchmark is a 0.3 ms kernel and may run before the clocks ramp: keep its per-clock rate and evaluate
-    # the peak at the SM clock sampled during the timed region
+    # the micro-benchmark is a sub-millisecond kernel and may run before the clocks ramp: keep its per-clock rate and
+    # evaluate the peak at the SM clock sampled during the timed region
     cells_per_clk = cell_peak / (mb_mhz * 1e6)
     load_mhz = (clocks or {}).get("sm_mhz") or mb_mhz
     cell_peak = cells_per_clk * load_mhz * 1e6
-    step_ms = elapsed_ms / args.steps
+    sm_count = w.plan.info()["sm_count"]
     compute = {"unit": "reference-equivalent DP cells/s", "cells_per_read": cells_per_read,
                "full_window_fraction": full / (2.0 * ncells_sample),
                "achieved": cells_per_read * n / (step_ms * 1e-3),
-               "peak": cell_peak, "peak_source": "qcb_microbench_cell_rate (add + VIMNMX3.U16x2 per 2 cells, same box)",
-               "peak_sm_mhz": load_mhz, "peak_cells_per_clk_per_sm": cells_per_clk / plan.info()["sm_count"]}
+               "peak": cell_peak,
+               "peak_source": "qcb_microbench_cell_rate: IMAD.IADD + VIMNMX3.U16x2 per 2 cells (the pair in the kernels' "
+                              "SASS, profiles/sass_k_barcode_fast_r02.txt), same box",
+               "peak_sm_mhz": load_mhz, "peak_cells_per_clk_per_sm": cells_per_clk / sm_count,
+               "peak_warp_inst_per_clk_per_sm": cells_per_clk / sm_count / 32.0}
     compute["frac"] = compute["achieved"] / cell_peak
-    if args.mode == "epi2me" and tables.n_groups >= 1 and len(set(int(tables.group_off[g + 1] - tables.group_off[g]) for g in range(tables.n_groups))) == 1:
+    uniform = len(set(int(tables.group_off[g + 1] - tables.group_off[g]) for g in range(tables.n_groups))) == 1
+    if w.spec["mode"] == "epi2me" and not w.spec.get("auto") and tables.n_groups >= 1 and uniform:
         # cells the packed kernels actually execute: adapters in full, but per barcode only the 24 core columns + the
         # join, and the shared prefix / suffix once per window (DESIGN.md section 4)
         nb = int(tables.group_off[1] - tables.group_off[0])
@@ -374,67 +499,199 @@ def run_ours(args):
         compute["executed_achieved"] = kernel_cells * n / (step_ms * 1e-3)
         compute["executed_frac"] = compute["executed_achieved"] / cell_peak
         if dom == "barcode" and not args.force_generic:
-            # What binds k_barcode_fast (ncu: LSU wavefronts 93 % of peak): every cell pair needs one 32-bit
+            # What binds k_barcode_fast (ncu: LSU wavefronts > 90 % of peak): every cell pair needs one 32-bit
             # substitution word gathered from shared memory by the lane's own base code, and the crossbar delivers 4 B
             # per lane per clock -- one wavefront per warp (32 windows x one barcode pair) per core column, plus one for
             # the row-info word.  Peak = 1 wavefront / clock / SM at the SM clock sampled under load.
             wavefronts_per_read = region_rows * (nb / 2.0) * 25.0 / 32.0
-            peak_wf = plan.info()["sm_count"] * load_mhz * 1e6
+            peak_wf = sm_count * load_mhz * 1e6
             achieved_wf = wavefronts_per_read * n / (dom_ms * 1e-3)
             compute["smem_gather_roofline"] = {"kernel": "k_barcode_fast", "unit": "shared-memory wavefronts/s",
                                                "wavefronts_per_read": wavefronts_per_read, "achieved": achieved_wf,
                                                "peak": peak_wf, "frac": achieved_wf / peak_wf,
-                                               "evidence": "profiles/r01d_barcode_full.md"}
+                                               "evidence": "profiles/r02_barcode_full.md"}
+    return compute
+
+
+def sharded_parity(w, n_common=65539):
+    """N > 1: one common dataset (same seed on every rank) is sharded round-robin with dist.shard_indices, every rank
+    scores its shard, the records are all-gathered and interleaved back with dist.unshard; rank 0 checks them against
+    its own 1-GPU run of the whole dataset and the gathered histogram against the records (scanner_base.py:714-733:
+    results in input order; cli.py:386-405: the counts)."""
+    import torch.distributed as tdist
+    from qcat_b200 import _ffi
+    from qcat_b200 import dist as qdist
+    from tests import helpers
+    torch = w.torch
+    common, _ = synth_batch(w.spec, w.sc, n_common, 0, seed=[20261017, 99])
+    idx = qdist.shard_indices(n_common, w.rank, w.world)
+    mine = w.plan.detect(common["win5"][idx], common["tail3"][idx], common["wlen"][idx], common["read_len"][idx])
+    per = (n_common + w.world - 1) // w.world
+    padded = np.zeros(per, dtype=_ffi.RESULT_DTYPE)
+    padded[:len(mine)] = mine
+    t = torch.from_numpy(padded.view(np.uint8).copy()).to(w.dev)
+    gathered = [torch.zeros_like(t) for _ in range(w.world)]
+    tdist.all_gather(gathered, t)
+    counts = torch.from_numpy(qdist.histogram_bins(mine, w.base, w.n_bins)).to(w.dev)
+    total = qdist.allgather_counts(counts).sum(0).cpu().numpy()
+    if w.rank != 0:
+        return None
+    shards = [g.cpu().numpy().view(_ffi.RESULT_DTYPE)[:len(qdist.shard_indices(n_common, r, w.world))] for r, g in enumerate(gathered)]
+    merged = qdist.unshard(shards, n_common)
+    single = w.plan.detect(common["win5"], common["tail3"], common["wlen"], common["read_len"])
+    helpers.assert_records_equal(merged, single, "N-GPU sharded records vs 1-GPU records")
+    np.testing.assert_array_equal(total, qdist.histogram_bins(single, w.base, w.n_bins))
+    head = helpers.oracle_detect(w.tables, common["win5"][:2000], common["tail3"][:2000], common["wlen"][:2000], common["read_len"][:2000])
+    helpers.assert_records_equal(merged[:2000], head, "N-GPU sharded records vs oracle")
+    return ("%d reads sharded round-robin over %d ranks (dist.shard_indices / unshard): records and gathered histogram "
+            "identical to the 1-GPU run; first 2000 identical to the CPU oracle" % (n_common, w.world))
+
+
+def strong_scaling(w, total_reads):
+    """Fixed job: total_reads reads split over the ranks (each rank's share = its unique reads tiled), one timed pass."""
+    torch = w.torch
+    share = (total_reads + w.world - 1) // w.world
+    reps = (share + w.n - 1) // w.n
+    d_in = tuple(torch.cat([t] * reps)[:share].contiguous() if reps > 1 else t[:share]
+                 for t in (w.d_win5, w.d_tail3, w.d_wlen, w.d_rlen))
+    d_out = torch.zeros(share * 32, dtype=torch.uint8, device=w.dev)
+    w.step(share, d_in, d_out)
+    w.barrier()
+    w.d_counts.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    w.step(share, d_in, d_out)
+    if w.world > 1:
+        import torch.distributed as dist
+        gathered = [torch.zeros_like(w.d_counts) for _ in range(w.world)]
+        dist.all_gather(gathered, w.d_counts)
+        total = int(torch.stack(gathered).sum().item())
+    else:
+        total = int(w.d_counts.sum().item())
+    e1.record()
+    w.barrier()
+    ms = w.max_over_ranks(e0.elapsed_time(e1))
+    assert total == share * w.world
+    del d_in, d_out
+    torch.cuda.empty_cache()
+    return {"scaling": "strong", "total_reads": share * w.world, "reads_per_gpu": share, "ms": ms,
+            "value": share * w.world / (ms * 1e-3), "unit": "reads/s",
+            "data": "each rank's %d unique reads tiled to its share" % w.unique}
+
+
+def measure_extra(name, args, rank, world, torch, dev, local_rank):
+    """One of the non-headline BASELINE configs: device-resident rate, e2e, stage times, parity spot check."""
+    w = Workload(name, args, rank, world)
+    w.to_device(torch, dev, local_rank)
+    try:
+        elapsed_ms, _, launches = w.timed(args.extra_steps, 3)
+        step_ms = elapsed_ms / args.extra_steps
+        stages = w.stage_profile()
+        res = {"config": workload_config(name, w.spec, w.n), "value": world * w.n / (step_ms * 1e-3), "unit": "reads/s",
+               "ms_per_step": step_ms, "steps": args.extra_steps, "gpu_launches": launches,
+               "stage_ms_per_step": {k: v[0] for k, v in stages.items()},
+               "data": "synthetic, %d unique reads per GPU per step (generated in %.1f s)" % (w.unique, w.gen_s)}
+        dom, roof = hbm_roofline(w, stages, args)
+        res["roofline"] = {k: roof[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "kernel_share_of_step")}
+        if not args.skip_e2e:
+            res["e2e"], out_view = w.e2e(2)
+            records = out_view
+        else:
+            from qcat_b200 import _ffi
+            records = w.d_out.cpu().numpy().view(_ffi.RESULT_DTYPE)
+        if rank == 0:
+            res["parity"] = w.parity_head(records)
+            from tests import helpers
+            m = min(w.n, 20000)
+            cells, full = helpers.oracle_count_cells(w.tables, w.batch["win5"][:m], w.batch["tail3"][:m], w.batch["wlen"][:m])
+            res["cells_per_read"] = cells / m
+            res["full_window_fraction"] = full / (2.0 * m)
+            res["classified_fraction"] = float((records["barcode"] >= 0).mean())
+            if w.spec.get("trim_check"):
+                res["trims"] = w.trim_check(records)
+        return res
+    finally:
+        w.free_device()
+
+
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # the synthetic shard is drawn by forked numpy workers: before this process touches CUDA
+    head = Workload(args.workload, args, rank, world)
+    log("rank %d: %d reads generated in %.1f s" % (rank, head.n, head.gen_s))
+
+    import torch
+    import torch.distributed as dist
+    from qcat_b200 import _ffi
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    head.to_device(torch, dev, local_rank)
+    n = head.n
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    elapsed_ms, total_counts, launches = head.timed(args.steps, args.warmup, sampler)
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = elapsed_ms / args.steps
+    value = world * n * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- per-stage profile (outside the timed region): dominant kernel and its roofline -------------
+    stages = head.stage_profile()
+    dom, roofline = hbm_roofline(head, stages, args)
+    compute = compute_roofline(head, step_ms, dom, stages[dom][0], clocks, local_rank, args) if rank == 0 else None
 
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside) ------------
     e2e = None
     if not args.skip_e2e:
-        h = {k: torch.from_numpy(batch[k]).pin_memory() for k in ("win5", "tail3", "wlen", "read_len")}
-        h_out = torch.zeros(n * 32, dtype=torch.uint8).pin_memory()
-        hv = {k: v.numpy() for k, v in h.items()}
-        out_view = h_out.numpy().view(_ffi.RESULT_DTYPE)
-        for _ in range(2):
-            plan.detect(hv["win5"], hv["tail3"], hv["wlen"], hv["read_len"], out=out_view)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            plan.detect(hv["win5"], hv["tail3"], hv["wlen"], hv["read_len"], out=out_view)
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * args.steps / float(dt.item()), "unit": "reads/s",
-               "h2d_bytes_per_step": int(n * (2 * stride + 4 + 8)), "d2h_bytes_per_step": int(n * 32),
-               "api": "qcb_detect (C ABI, pinned host buffers)"}
-        gpu_head = out_view[:2000].copy()
+        e2e, out_view = head.e2e(args.steps)
+        records = out_view
     else:
-        gpu_head = d_out[:2000 * 32].cpu().numpy().view(_ffi.RESULT_DTYPE)
+        records = head.d_out.cpu().numpy().view(_ffi.RESULT_DTYPE)
 
-    # ---- parity spot check + CPU baseline (rank 0) --------------------------------------------------
+    # ---- parity spot check, N-GPU == 1-GPU, strong scaling, CPU baseline ---------------------------------
+    parity = head.parity_head(records) if rank == 0 else None
+    sharded = sharded_parity(head) if world > 1 else None
+    strong = strong_scaling(head, args.strong_reads) if args.strong_reads > 0 else None
     cpu = None
-    parity = None
-    if rank == 0:
-        want = helpers.oracle_detect(tables, batch["win5"][:2000], batch["tail3"][:2000], batch["wlen"][:2000], batch["read_len"][:2000])
-        helpers.assert_records_equal(gpu_head, want, "bench parity spot check")
-        parity = "2000 records bit-identical to the CPU oracle"
-        if world == 1 and not args.skip_cpu_baseline:
-            threads = os.cpu_count() or 1
-            rate, m, _ = cpu_oracle_rate(tables, batch, args.cpu_sample, threads)
-            cpu = {"value": rate, "unit": "reads/s", "cores": threads, "kind": "port",
-                   "sample": "first %d reads of the step batch, C oracle port (scalar int32 affine DP), OpenMP over reads" % m,
-                   "reference_python": reference_python_rate(args, batch)}
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, m = cpu_oracle_rate(head.spec, head.sc, head.tables, head.batch, args.cpu_sample, threads)
+        cpu = {"value": rate, "unit": "reads/s", "cores": threads, "kind": "port",
+               "sample": "first %d reads of the step batch, C oracle port (scalar int32 affine DP), OpenMP over reads" % m,
+               "reference_python": reference_python_rate(head.spec, head.batch)}
+    info = head.plan.info()
+    head_data = "synthetic (%d unique reads per GPU per step, generated in %.1f s)" % (head.unique, head.gen_s)
+    head.free_device()
+
+    # ---- the other BASELINE configs -------------------------------------------------------------------------
+    extras = {}
+    for name in [x for x in args.extra_workloads.split(",") if x]:
+        if name == args.workload:
+            continue
+        try:
+            extras[name] = measure_extra(name, args, rank, world, torch, dev, local_rank)
+            if rank == 0:
+                log("%s: %.2f M reads/s" % (name, extras[name]["value"] / 1e6))
+        except Exception as exc:                                # noqa: BLE001 -- reported, the headline stands
+            if world > 1:
+                raise                                           # ranks must stay in step: fail loudly
+            extras[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     if rank == 0:
-        info = plan.info()
-        line = {"metric": "reads/s demuxed (96-barcode EPI2ME, 150bp windows)", "value": value, "unit": "reads/s",
-                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
+        line = {"metric": METRIC, "value": value, "unit": "reads/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16x2 (packed DP) / int32 / f64 scores",
-                "data": "synthetic (%d unique reads tiled to %d per GPU per step)" % (min(n, args.unique_reads), n),
-                "config": workload_config(args, n), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "data": head_data,
+                "config": workload_config(args.workload, head.spec, n), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "compute_roofline": compute, "cpu_baseline": cpu, "parity": parity,
+                "sharded_parity": sharded, "strong_scaling": strong, "workloads": extras,
                 "kernels": {"fast_adapter": info["fast_adapter"], "fast_barcode": info["fast_barcode"]}}
         emit_result(line)
-    plan.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -448,11 +705,6 @@ def main():
     _RESULT_FD = os.dup(1)
     os.dup2(2, 1)
     args = parse_args()
-    kit, mode, _ = WORKLOADS[args.workload]
-    if args.mode is None:
-        args.mode = mode
-    if args.kit is None and args.mode != "dual":
-        args.kit = kit
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -10,7 +10,7 @@
  *     extract_barcode_region (:29-60), find_highest_scoring_barcode (:63-141),
  *     BarcodeScannerEPI2ME.scan (scanner_epi2me.py:33-144), BarcodeScannerDual.scan
  *     (scanner_dual.py:35-146) and BarcodeScanner.detect_barcode (scanner_base.py:521-604),
- *     batched over reads as in detect_barcode_batch (:714-733)              -> qcb_detect*()
+ *     batched over reads as in detect_barcode_batch (:714-733)              -> qcb_detect*(), qcb_detect_auto*()
  *   - detect_kit's per-read vote (scanner_base.py:618-678)                  -> qcb_kit_vote*()
  *   - the per-barcode counts behind the CLI histogram (cli.py:386-405)      -> qcb_histogram_device()
  *   - host only, either side of the path: record iteration (cli.py:235-306), window extraction
@@ -151,6 +151,22 @@ int qcb_kit_vote(qcb_plan *plan, const uint8_t *win5, const uint8_t *tail3, int3
 
 int qcb_kit_vote_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t *d_tail3, int32_t stride,
                         const int32_t *d_wlen, int64_t n_reads, int32_t *d_vote_layout, void *stream);
+
+/* detect_barcode_batch with more than one kit among the layouts (scanner_base.py:714-733; `-k auto`, the CLI default) in
+ * ONE pass: the adapter stage runs once over all layouts, its scores give every read's vote (scan_ends, :632-642), every
+ * batch of `batch_size` consecutive reads (cli.py:500: 4000) elects its kit on the device (most votes; ties: the kit
+ * seen first in the batch, :657-660), and detection continues restricted to that kit's layouts on the adapter scores
+ * already computed.  kit_of_layout: host array [n_layouts], kit index (0 .. 255) of every layout.  batch_kit (may be
+ * NULL): [ceil(n_reads / batch_size)] elected kit per batch -- host memory for qcb_detect_auto, device memory for the
+ * _device variant.  Results equal qcb_kit_vote + per-batch qcb_detect with the kit's layouts as subset. */
+int qcb_detect_auto(qcb_plan *plan, const uint8_t *win5, const uint8_t *tail3, int32_t stride,
+                    const int32_t *wlen, const int64_t *read_len, int64_t n_reads,
+                    const int32_t *kit_of_layout, int32_t batch_size, qcb_result *out, int32_t *batch_kit);
+
+int qcb_detect_auto_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t *d_tail3, int32_t stride,
+                           const int32_t *d_wlen, const int64_t *d_read_len, int64_t n_reads,
+                           const int32_t *kit_of_layout /* host */, int32_t batch_size, qcb_result *d_out,
+                           int32_t *d_batch_kit, void *stream);
 
 /* counts[bin] += 1 per record, bin = 0 for "none", 1 + layout_bin_base[layout] + barcode otherwise
  * (layout_bin_base: host array [n_layouts]).  d_counts must hold n_bins int64 and is NOT cleared. */

@@ -77,6 +77,75 @@ void qo_sg(const uint8_t *s1, int n, const uint8_t *s2, int m, int open, int ext
     free(H);
 }
 
+/*
+ * parasail `sg_stats` (parasail.sg_stats_striped_32, bound at scanner_base.py:20-26, used by
+ * find_highest_scoring_barcode(compute_identity=True) :106-123 -- the simple scanner -- and by align_adapter_identity
+ * :144-188): the same recurrence as qo_sg plus, carried along the path the recurrence takes, the number of exact
+ * matches, of positive-scoring ("similar") columns and the alignment length.
+ * Score and end cell: identical to qo_sg (same end-cell rule, same "parity unpinned" status).
+ * matches / similar / length depend on which of several equal-scoring predecessors the recurrence follows; restated
+ * from parasail 2.x's scalar sg_stats from memory, pinned by NO reference test ("parity unpinned"): a gap is opened
+ * only when opening is strictly better than extending; H takes the diagonal when it is >= both gap states, else the
+ * F (gap in the template direction, from the row above) state when F >= E, else E.  Exact matches compare the
+ * mapped character codes.  Nothing on qcat's result path reads these counters: the simple scanner's `identity` is
+ * overwritten by the score before it is used (scanner_base.py:141 returns max_score in its place).
+ */
+void qo_sg_stats(const uint8_t *s1, int n, const uint8_t *s2, int m, int open, int extend,
+                 const int32_t *matrix, int msize, const uint8_t *mapper,
+                 int32_t *score, int32_t *end_query, int32_t *end_ref,
+                 int32_t *matches, int32_t *similar, int32_t *length)
+{
+    *matches = 0; *similar = 0; *length = 0;
+    if (n <= 0 || m <= 0) { *score = 0; *end_query = -1; *end_ref = -1; return; }
+    typedef struct { int32_t h, m, s, l; } cell;
+    cell *H = (cell *)calloc((size_t)(m + 1), sizeof(cell));       /* H[i-1][*] then H[i][*] */
+    cell *F = (cell *)calloc((size_t)(m + 1), sizeof(cell));
+    cell *lastcol = (cell *)calloc((size_t)(n + 1), sizeof(cell)); /* H[i][m] for the end-cell rule */
+    int32_t *c2 = (int32_t *)malloc(sizeof(int32_t) * (size_t)m);
+    for (int j = 0; j < m; ++j) c2[j] = mapper[s2[j]];
+    for (int j = 0; j <= m; ++j) F[j].h = QO_NEG_INF;
+    int32_t col_max = INT32_MIN, col_arg = -1;
+    for (int i = 1; i <= n; ++i) {
+        const int c1 = mapper[s1[i - 1]];
+        const int32_t *row = matrix + (size_t)msize * c1;
+        cell diag = H[0];                          /* H[i-1][0]: zero border */
+        cell left; left.h = 0; left.m = 0; left.s = 0; left.l = 0;
+        cell E; E.h = QO_NEG_INF; E.m = 0; E.s = 0; E.l = 0;
+        for (int j = 1; j <= m; ++j) {
+            cell up = H[j];
+            cell f, e, h;
+            if (up.h - open > F[j].h - extend) { f = up; f.h = up.h - open; } else { f = F[j]; f.h = F[j].h - extend; }
+            f.l += 1;
+            if (left.h - open > E.h - extend) { e = left; e.h = left.h - open; } else { e = E; e.h = E.h - extend; }
+            e.l += 1;
+            int32_t sub = row[c2[j - 1]];
+            int32_t d = diag.h + sub;
+            if (d >= e.h && d >= f.h) {
+                h.h = d; h.m = diag.m + (c1 == c2[j - 1]); h.s = diag.s + (sub > 0); h.l = diag.l + 1;
+            } else if (f.h >= e.h) h = f;
+            else h = e;
+            F[j] = f; E = e;
+            diag = up;
+            H[j] = h;
+            left = h;
+        }
+        lastcol[i] = H[m];
+        if (H[m].h > col_max) { col_max = H[m].h; col_arg = i; }
+    }
+    int32_t row_max = INT32_MIN, row_arg = -1;
+    for (int j = 1; j <= m; ++j)
+        if (H[j].h > row_max) { row_max = H[j].h; row_arg = j; }
+    cell end;
+    if (col_max > row_max) {
+        *score = col_max; *end_query = col_arg - 1; *end_ref = m - 1; end = lastcol[col_arg];
+    } else {
+        *score = row_max; *end_ref = row_arg - 1; *end_query = n - 1; end = H[row_arg];
+        if (row_arg == m) { *end_query = col_arg - 1; end = lastcol[col_arg]; }
+    }
+    *matches = end.m; *similar = end.s; *length = end.l;
+    free(c2); free(lastcol); free(F); free(H);
+}
+
 /* Python slice semantics seq[start:stop] on a sequence of length n -> [lo, hi) (possibly empty). */
 static void py_slice(int start, int stop, int n, int *lo, int *hi)
 {
@@ -154,9 +223,39 @@ static scan_result empty_scan(void)      /* empty_return_dict, scanner_base.py:3
     scan_result r; r.layout = -1; r.barcode = -1; r.ident = -1; r.score = 0.0; r.adapter_end = 0; return r;
 }
 
+/* BarcodeScannerSimple.scan (scanner_simple.py:47-92): every barcode of self.barcodes (template group 0: the bare
+ * barcode sequences, no context) against the whole window with sg_stats; find_highest_scoring_barcode's first-maximum
+ * rule (:119-134) also keeps the end_query of the winner (`max_end`).  What scan() calls `identity` is the third
+ * value returned at :141 -- max_score, not the identity -- so the threshold compares the score. */
+static scan_result scan_window_simple(const qo_tables *t, const uint8_t *win, int n)
+{
+    int have = 0; double max_score = 0.0; int max_idx = -1, max_end = -1;
+    double identity = 0.0;                                     /* :101: (None, 0, 0.0, -1) for an empty window */
+    if (n > 0) {
+        for (int b = t->group_off[0]; b < t->group_off[1]; ++b) {
+            int tl = t->tmpl_off[b + 1] - t->tmpl_off[b];
+            int32_t sc, eq, er, mt, sm, ln;
+            qo_sg_stats(win, n, t->tmpl_seq + t->tmpl_off[b], tl, t->barcode_open, t->barcode_extend,
+                        t->bmat, t->bmat_size, t->bmap, &sc, &eq, &er, &mt, &sm, &ln);
+            double score = (double)sc * 100.0 / (1.0 * (double)tl);
+            if (!have || max_score == 0.0 || max_score < score) { have = 1; max_score = score; max_idx = b - t->group_off[0]; max_end = eq; }
+        }
+        identity = max_score;                                  /* :141 */
+    }
+    if (identity < t->min_quality) return empty_scan();        /* scanner_simple.py:81-82 */
+    scan_result r;
+    r.layout = -1;                                             /* best_adapter=None */
+    r.barcode = max_idx;
+    r.ident = max_idx >= 0 ? t->tmpl_ident[t->group_off[0] + max_idx] : -1;
+    r.score = max_score;                                       /* q_score = max_score (:139) */
+    r.adapter_end = max_end;                                   /* best_adapter_end=barcode_end */
+    return r;
+}
+
 /* BarcodeScannerEPI2ME.scan (scanner_epi2me.py:33-144) and BarcodeScannerDual.scan (scanner_dual.py:35-146). */
 static scan_result scan_window(const qo_tables *t, const int32_t *subset, int n_subset, const uint8_t *win, int n)
 {
+    if (t->mode == 2) return scan_window_simple(t, win, n);
     int32_t idx, end; double ascore;
     qo_find_best_adapter_template(t, subset, n_subset, win, n, &idx, &end, &ascore);
     int L = subset[idx < 0 ? n_subset + idx : idx];           /* Python negative index: -1 -> last (:64) */
@@ -271,7 +370,7 @@ void qo_scan(const qo_tables *t, const uint8_t *windows, int64_t stride, const i
         scan_result r = scan_window(t, subset, n_subset, windows + (size_t)w * (size_t)stride, wlen[w]);
         out[w].layout = r.layout; out[w].barcode = r.barcode; out[w].barcode_score = r.score;
         out[w].adapter_end = r.adapter_end; out[w].trim5p = 0; out[w].trim3p = 0;
-        out[w].exit_status = r.layout < 0 ? 1 : 0;
+        out[w].exit_status = (r.layout < 0 && r.barcode < 0) ? 1 : 0;
     }
     free(all);
 }

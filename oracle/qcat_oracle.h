@@ -43,7 +43,8 @@ typedef struct {
     const uint8_t *bmap;
     const uint8_t *comp;        /* 256-entry complement table (utils.py:26-27) */
     /* scanner */
-    int32_t mode;               /* 0 = epi2me (scanner_epi2me.py), 1 = dual (scanner_dual.py) */
+    int32_t mode;               /* 0 = epi2me (scanner_epi2me.py), 1 = dual (scanner_dual.py), 2 = simple (scanner_simple.py:
+                                 * template group 0 = the bare barcodes of self.barcodes, one placeholder layout) */
     double min_quality;         /* 58 epi2me / 60 dual unless overridden */
     /* layouts, in self.layouts order */
     int32_t n_layouts;
@@ -79,6 +80,13 @@ typedef struct {
 void qo_sg(const uint8_t *s1, int n, const uint8_t *s2, int m, int open, int extend,
            const int32_t *matrix, int msize, const uint8_t *mapper,
            int32_t *score, int32_t *end_query, int32_t *end_ref);
+
+/* parasail sg_stats (scanner_base.py:20-26, :106-123, :168-172): qo_sg plus matches / similar / length of the path the
+ * recurrence follows ("parity unpinned" for those three, see qcat_oracle.c). */
+void qo_sg_stats(const uint8_t *s1, int n, const uint8_t *s2, int m, int open, int extend,
+                 const int32_t *matrix, int msize, const uint8_t *mapper,
+                 int32_t *score, int32_t *end_query, int32_t *end_ref,
+                 int32_t *matches, int32_t *similar, int32_t *length);
 
 /* find_best_adapter_template (scanner_base.py:313-359) over layouts[subset[0..n_subset)]. */
 void qo_find_best_adapter_template(const qo_tables *t, const int32_t *subset, int n_subset,

@@ -3,7 +3,7 @@
 Lets the UNMODIFIED reference Python under /root/reference import and run: it binds
 `parasail.sg_striped_32`, `parasail.sg_stats_striped_32`, `parasail.can_use_sse2` at import
 (scanner_base.py:20-26) and `parasail.matrix_create` + pokes into `.pointer[0].matrix[i]`
-(config.py:26, 245-253).  The alignment itself is the C oracle's qo_sg().
+(config.py:26, 245-253).  The alignment itself is the C oracle's qo_sg() / qo_sg_stats().
 """
 import ctypes
 import os
@@ -56,8 +56,12 @@ def can_use_sse2():
     return True
 
 
+_lib.qo_sg_stats.restype = None
+_lib.qo_sg_stats.argtypes = _lib.qo_sg.argtypes + [ctypes.POINTER(ctypes.c_int32)] * 3
+
+
 class Result(object):
-    __slots__ = ("score", "end_query", "end_ref")
+    __slots__ = ("score", "end_query", "end_ref", "matches", "similar", "length")
 
 
 def _as_bytes(s):
@@ -78,8 +82,17 @@ def sg(s1, s2, open, extend, matrix):
 sg_striped_32 = sg
 
 
-def sg_stats(*a, **k):
-    raise NotImplementedError("sg_stats is only used by qcat's out-of-scope 'simple' mode")
+def sg_stats(s1, s2, open, extend, matrix):
+    """parasail.sg_stats*: used by qcat's simple scanner (find_highest_scoring_barcode(compute_identity=True)) and
+    by align_adapter_identity.  Backed by the oracle's qo_sg_stats."""
+    b1, b2 = _as_bytes(s1), _as_bytes(s2)
+    m = matrix.pointer[0]
+    out = [ctypes.c_int32() for _ in range(6)]
+    _lib.qo_sg_stats(b1, len(b1), b2, len(b2), int(open), int(extend), m.matrix, m.size, m.mapper,
+                     *[ctypes.byref(v) for v in out])
+    r = Result()
+    r.score, r.end_query, r.end_ref, r.matches, r.similar, r.length = [v.value for v in out]
+    return r
 
 
 sg_stats_striped_32 = sg_stats

@@ -70,6 +70,7 @@ struct qcb_plan {
     FastPlan fast;                   // packed-kernel tables (kernels_fast.cuh)
     // workspace, sized per chunk of reads
     DeviceBuffer wins, codes, ad_score, ad_end, sel, bc_score, subset_dev, misc, long_part, long_row;
+    DeviceBuffer auto_vote, auto_kit, auto_map;   // auto-kit flow: per-read vote, per-batch kit, layout -> kit table
     int long_ov = 0;                 // warm-up rows of k_adapter_long (0 = chunking not provably exact for these tables)
     cudaStream_t stream = nullptr;   // kernels of the host-buffer entry points
     cudaStream_t copy_in = nullptr, copy_out = nullptr;      // H2D / D2H of the host-buffer entry points
@@ -212,10 +213,21 @@ struct StageTimer {
     }
 };
 
+// Auto-kit flow of one call (detect_barcode_batch with several kits, scanner_base.py:714-733): the adapter stage runs
+// once over all layouts; its scores feed the per-read vote, the per-batch kit and then the kit-restricted selection.
+struct AutoKit {
+    const int32_t *d_kit_of_layout;   // [n_layouts] kit index of every layout
+    int n_kits;
+    int batch_size;                   // reads per CLI batch (4000)
+    int32_t *d_batch_kit;             // [batches of the call] winning kit
+    long long read_offset;            // index of the chunk's first read inside the call
+    bool have_kits;                   // d_batch_kit is already filled (batches larger than a chunk: voted in a first pass)
+};
+
 // d_tail3 == nullptr selects window mode: d_win5 holds n already-oriented windows (BarcodeScanner.scan).
 int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int stride, const int32_t *d_wlen,
               const int64_t *d_read_len, long long n, const int32_t *d_subset, const int32_t *h_subset, int n_subset,
-              qcb_result *d_out, int32_t *d_vote, cudaStream_t st)
+              qcb_result *d_out, int32_t *d_vote, cudaStream_t st, const AutoKit *autokit = nullptr)
 {
     const bool window_mode = d_tail3 == nullptr;
     const int wshift = window_mode ? 0 : 1;
@@ -280,13 +292,24 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
         QCB_CUDA(cudaGetLastError());
         return 0;
     }
+    if (autokit && !autokit->have_kits) {                // chunk = whole batches: vote and pick the kits right here
+        StageTimer timer(p, 4, st);
+        if (p->auto_vote.reserve((size_t)n * 4)) return 1;
+        int32_t *vote = (int32_t *)p->auto_vote.ptr;
+        k_kit_vote<<<grid_for(n, 256), 256, 0, st>>>(t, d_wlen, n, d_subset, n_subset, ad_score, ad_end, vote);
+        k_batch_kit<<<grid_for(n, autokit->batch_size), 256, 0, st>>>(vote, n, autokit->batch_size, autokit->d_kit_of_layout, autokit->n_kits,
+                                                                      autokit->d_batch_kit + autokit->read_offset / autokit->batch_size);
+        p->launches += 2;
+    }
     if (p->sel.reserve((size_t)nw * sizeof(WindowSel))) return 1;
     if (p->bc_score.reserve((size_t)nw * bslots * 4)) return 1;
     WindowSel *sel = (WindowSel *)p->sel.ptr;
     int32_t *bc_score = (int32_t *)p->bc_score.ptr;
     {
     StageTimer timer(p, 2, st);
-    k_select<<<grid_for(nw, 256), 256, 0, st>>>(t, d_wlen, wshift, nw, d_subset, n_subset, ad_score, ad_end, sel);
+    k_select<<<grid_for(nw, 256), 256, 0, st>>>(t, d_wlen, wshift, nw, d_subset, n_subset, ad_score, ad_end, sel,
+                                                autokit ? autokit->d_kit_of_layout : nullptr, autokit ? autokit->d_batch_kit : nullptr,
+                                                autokit ? autokit->batch_size : 1, autokit ? autokit->read_offset : 0);
     p->launches++;
     }
     if (fast_ok && p->fast.barcode_ok) {
@@ -328,9 +351,36 @@ int prepare_subset(qcb_plan *p, const int32_t *subset, int n_subset, std::vector
     return 0;
 }
 
+// Host description of an auto-kit call; d_batch_kit receives one kit index per batch of the whole call.
+struct AutoCall {
+    const int32_t *kit_of_layout;     // host, [n_layouts]
+    int batch_size;
+    int32_t *d_batch_kit;             // device, [ceil(n_reads / batch_size)] or NULL (plan-owned scratch is used)
+};
+
+int auto_prepare(qcb_plan *p, const AutoCall *ac, int64_t n_reads, int &n_kits, int32_t *&d_batch_kit, cudaStream_t st)
+{
+    if (!ac->kit_of_layout) return fail("kit_of_layout is NULL");
+    if (ac->batch_size <= 0) return fail("batch_size must be positive");
+    n_kits = 0;
+    for (int L = 0; L < p->t.n_layouts; ++L) {
+        if (ac->kit_of_layout[L] < 0 || ac->kit_of_layout[L] >= kMaxKits) return fail("kit_of_layout[%d] outside [0, %d)", L, kMaxKits);
+        n_kits = std::max(n_kits, ac->kit_of_layout[L] + 1);
+    }
+    if (p->auto_map.reserve((size_t)p->t.n_layouts * 4)) return 1;
+    QCB_CUDA(cudaMemcpyAsync(p->auto_map.ptr, ac->kit_of_layout, (size_t)p->t.n_layouts * 4, cudaMemcpyHostToDevice, st));
+    d_batch_kit = ac->d_batch_kit;
+    if (!d_batch_kit) {
+        const size_t nb = (size_t)((n_reads + ac->batch_size - 1) / ac->batch_size);
+        if (p->auto_kit.reserve(nb * 4)) return 1;
+        d_batch_kit = (int32_t *)p->auto_kit.ptr;
+    }
+    return 0;
+}
+
 int detect_device_impl(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int32_t stride, const int32_t *d_wlen,
                        const int64_t *d_read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset,
-                       qcb_result *d_out, int32_t *d_vote, cudaStream_t st)
+                       qcb_result *d_out, int32_t *d_vote, cudaStream_t st, const AutoCall *ac = nullptr)
 {
     if (!p) return fail("plan is NULL");
     if (n_reads < 0) return fail("n_reads is negative");
@@ -342,11 +392,36 @@ int detect_device_impl(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail
     const int32_t *d_subset = (const int32_t *)p->subset_dev.ptr;
     long long dev_chunk = p->chunk_reads;
     if ((long long)stride * dev_chunk > (1LL << 28)) dev_chunk = std::max<long long>(1, (1LL << 28) / stride);
+    AutoKit ak{};
+    if (ac) {
+        if (auto_prepare(p, ac, n_reads, ak.n_kits, ak.d_batch_kit, st)) return 1;
+        ak.d_kit_of_layout = (const int32_t *)p->auto_map.ptr;
+        ak.batch_size = ac->batch_size;
+        if (ac->batch_size <= dev_chunk) {
+            dev_chunk = dev_chunk / ac->batch_size * ac->batch_size;       // every chunk holds whole batches: one pass
+        } else {
+            // a batch spans several chunks: vote over the whole call first (adapter stage only), then the regular pass
+            if (p->auto_vote.reserve((size_t)n_reads * 4)) return 1;
+            int32_t *vote = (int32_t *)p->auto_vote.ptr;
+            int rc = 0;
+            for (long long off = 0; off < n_reads && !rc; off += dev_chunk) {
+                long long n = std::min<long long>(dev_chunk, n_reads - off);
+                rc = run_chunk(p, d_win5 + off * stride, d_tail3 + off * stride, stride, d_wlen + off, nullptr, n, d_subset,
+                               h_subset.data(), (int)h_subset.size(), nullptr, vote + off, st);
+            }
+            if (rc) return 1;
+            k_batch_kit<<<grid_for(n_reads, ac->batch_size), 256, 0, st>>>(vote, n_reads, ac->batch_size, ak.d_kit_of_layout, ak.n_kits,
+                                                                          ak.d_batch_kit);
+            p->launches++;
+            ak.have_kits = true;
+        }
+    }
     for (long long off = 0; off < n_reads; off += dev_chunk) {
         long long n = std::min<long long>(dev_chunk, n_reads - off);
+        ak.read_offset = off;
         if (run_chunk(p, d_win5 + off * stride, d_tail3 ? d_tail3 + off * stride : nullptr, stride, d_wlen + off,
                       d_read_len ? d_read_len + off : nullptr, n, d_subset, h_subset.data(), (int)h_subset.size(),
-                      d_out ? d_out + off : nullptr, d_vote ? d_vote + off : nullptr, st))
+                      d_out ? d_out + off : nullptr, d_vote ? d_vote + off : nullptr, st, ac ? &ak : nullptr))
             return 1;
     }
     return 0;
@@ -358,7 +433,8 @@ int detect_device_impl(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail
 // the copies truly asynchronous; pageable memory still works, just without the overlap).
 int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int32_t stride, const int32_t *wlen,
                      const int64_t *read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset,
-                     qcb_result *out, int32_t *vote)
+                     qcb_result *out, int32_t *vote, const int32_t *kit_of_layout = nullptr, int32_t batch_size = 0,
+                     int32_t *batch_kit_out = nullptr)
 {
     if (!p) return fail("plan is NULL");
     if (n_reads < 0) return fail("n_reads is negative");
@@ -377,6 +453,14 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
     long long chunk = std::max<long long>(p->host_chunk_reads, (n_reads / 8 + 31) / 32 * 32);
     chunk = std::min<long long>(chunk, p->chunk_reads);
     if ((long long)stride * chunk > (1LL << 27)) chunk = std::max<long long>(1, (1LL << 27) / stride);
+    const bool auto_mode = kit_of_layout != nullptr;
+    const long long n_batches = auto_mode ? (n_reads + batch_size - 1) / batch_size : 0;
+    if (auto_mode) {
+        // pipeline chunks are whole batches; a batch larger than a chunk goes to the device in one piece
+        if (batch_size <= 0) return fail("batch_size must be positive");
+        chunk = batch_size <= chunk ? chunk / batch_size * batch_size : n_reads;
+        if (p->auto_kit.reserve((size_t)n_batches * 4)) return 1;
+    }
     const size_t out_item = vote ? 4 : sizeof(qcb_result);
     int rc = 0;
     long long k = 0;
@@ -410,9 +494,10 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
         if (!vote && !window_mode) { LOOP_CUDA(cudaMemcpyAsync(d + o_rl, read_len + off, b_rl, cudaMemcpyHostToDevice, s_in)); }
         LOOP_CUDA(cudaEventRecord(p->ev_h2d[b], s_in));
         LOOP_CUDA(cudaStreamWaitEvent(st, p->ev_h2d[b], 0));
+        AutoCall ac{kit_of_layout, batch_size, auto_mode ? (int32_t *)p->auto_kit.ptr + off / batch_size : nullptr};
         rc = detect_device_impl(p, d, window_mode ? nullptr : d + o_tail, stride, (const int32_t *)(d + o_len),
                                 (const int64_t *)(d + o_rl), n, subset, n_subset, vote ? nullptr : (qcb_result *)d_res,
-                                vote ? (int32_t *)d_res : nullptr, st);
+                                vote ? (int32_t *)d_res : nullptr, st, auto_mode ? &ac : nullptr);
         if (rc) break;
         LOOP_CUDA(cudaEventRecord(p->ev_compute[b], st));
         LOOP_CUDA(cudaStreamWaitEvent(s_out, p->ev_compute[b], 0));
@@ -421,6 +506,9 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
         LOOP_CUDA(cudaEventRecord(p->ev_d2h[b], s_out));
     }
 #undef LOOP_CUDA
+    if (!rc && auto_mode && batch_kit_out &&
+        cudaMemcpyAsync(batch_kit_out, p->auto_kit.ptr, (size_t)n_batches * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        rc = fail("copy of the per-batch kits failed");
     cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(s_out);
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
@@ -474,6 +562,7 @@ void qcb_plan_destroy(qcb_plan *p)
     fast_plan_free(p->fast);
     p->wins.release(); p->codes.release(); p->ad_score.release(); p->ad_end.release(); p->sel.release(); p->bc_score.release();
     p->subset_dev.release(); p->misc.release(); p->long_part.release(); p->long_row.release();
+    p->auto_vote.release(); p->auto_kit.release(); p->auto_map.release();
     if (p->slab) cudaFree(p->slab);
     for (int i = 0; i < 2; ++i) {
         p->in_stage2[i].release(); p->out_stage2[i].release();
@@ -595,6 +684,26 @@ int qcb_detect_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t *d_ta
     if (!d_win5 || !d_tail3 || !d_wlen || !d_read_len || !d_out) return n_reads == 0 ? 0 : fail("NULL device buffer");
     return detect_device_impl(plan, d_win5, d_tail3, stride, d_wlen, d_read_len, n_reads, subset, n_subset, d_out, nullptr,
                               (cudaStream_t)stream);
+}
+
+int qcb_detect_auto(qcb_plan *plan, const uint8_t *win5, const uint8_t *tail3, int32_t stride, const int32_t *wlen,
+                    const int64_t *read_len, int64_t n_reads, const int32_t *kit_of_layout, int32_t batch_size,
+                    qcb_result *out, int32_t *batch_kit)
+{
+    if (!kit_of_layout) return fail("kit_of_layout is NULL");
+    if (!tail3) return fail("NULL input/output buffer");
+    return detect_host_impl(plan, win5, tail3, stride, wlen, read_len, n_reads, nullptr, 0, out, nullptr, kit_of_layout, batch_size,
+                            batch_kit);
+}
+
+int qcb_detect_auto_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t *d_tail3, int32_t stride, const int32_t *d_wlen,
+                           const int64_t *d_read_len, int64_t n_reads, const int32_t *kit_of_layout, int32_t batch_size,
+                           qcb_result *d_out, int32_t *d_batch_kit, void *stream)
+{
+    if (!d_win5 || !d_tail3 || !d_wlen || !d_read_len || !d_out) return n_reads == 0 ? 0 : fail("NULL device buffer");
+    AutoCall ac{kit_of_layout, batch_size, d_batch_kit};
+    return detect_device_impl(plan, d_win5, d_tail3, stride, d_wlen, d_read_len, n_reads, nullptr, 0, d_out, nullptr,
+                              (cudaStream_t)stream, &ac);
 }
 
 int qcb_scan(qcb_plan *plan, const uint8_t *windows, int32_t stride, const int32_t *wlen, int64_t n_windows,

@@ -223,15 +223,18 @@ __device__ __forceinline__ void barcode_region(const DevTables &t, int L, int k,
 }
 
 // find_best_adapter_template's arg-max over the subset (scanner_base.py:330-359): strict '<', first wins,
-// nothing found -> index -1.  Returns the position inside the subset.
+// nothing found -> index -1.  Returns the position inside the subset.  kit >= 0 restricts the scan to the subset
+// entries whose layout belongs to that kit (the per-batch kit of the auto-kit flow, scanner_base.py:526-529).
 __device__ __forceinline__ void best_template(const DevTables &t, const int32_t *subset, int n_subset, int n,
                                               const int32_t *ad_score, const int32_t *ad_end,
-                                              int &best_idx, int &best_end, double &best_score)
+                                              int &best_idx, int &best_end, double &best_score,
+                                              const int32_t *kit_of_layout = nullptr, int kit = -1)
 {
     best_score = -1.0; best_end = -1; best_idx = -1;
     if (n <= 0) return;
     for (int s = 0; s < n_subset; ++s) {
         int L = subset[s];
+        if (kit >= 0 && kit_of_layout[L] != kit) continue;
         if (t.adapter_off[L + 1] - t.adapter_off[L] <= 0) continue;
         double norm = (double)ad_score[s] * 100.0 / t.denom[L];
         if (best_score < norm) { best_score = norm; best_idx = s; best_end = ad_end[s]; }
@@ -239,17 +242,26 @@ __device__ __forceinline__ void best_template(const DevTables &t, const int32_t 
 }
 
 // Template choice + barcode-region geometry per window (scanner_epi2me.py:57-82, scanner_dual.py:57-110).
+// Auto-kit flow (batch_kit != nullptr): the layouts considered for read r are those of kit batch_kit[r / batch_size],
+// the kit its CLI batch voted for -- the adapter scores of all layouts are already in ad_score / ad_end.
 __global__ void k_select(DevTables t, const int32_t *__restrict__ wlen, int wshift, long long n_windows,
                          const int32_t *__restrict__ subset, int n_subset,
                          const int32_t *__restrict__ ad_score, const int32_t *__restrict__ ad_end,
-                         WindowSel *__restrict__ sel)
+                         WindowSel *__restrict__ sel,
+                         const int32_t *__restrict__ kit_of_layout, const int32_t *__restrict__ batch_kit, int batch_size,
+                         long long read_offset)
 {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_windows) return;
     int n = wlen[w >> wshift];
+    const int kit = batch_kit ? batch_kit[(read_offset + (w >> wshift)) / batch_size] : -1;
     int idx, end; double ascore;
-    best_template(t, subset, n_subset, n, ad_score + w * n_subset, ad_end + w * n_subset, idx, end, ascore);
-    int L = subset[idx < 0 ? n_subset + idx : idx];     // Python negative index: -1 -> last layout
+    best_template(t, subset, n_subset, n, ad_score + w * n_subset, ad_end + w * n_subset, idx, end, ascore, kit_of_layout, kit);
+    if (idx < 0) {                                      // Python negative index: -1 -> last layout (of the kit)
+        idx = n_subset - 1;
+        if (kit >= 0) while (idx > 0 && kit_of_layout[subset[idx]] != kit) --idx;
+    }
+    int L = subset[idx];
     WindowSel s;
     s.layout = L; s.end_query = end; s.lo1 = 0; s.hi1 = 0; s.full = 0; s.pad = 0;
     if (t.mode == QCB_MODE_EPI2ME) {
@@ -412,6 +424,32 @@ __global__ void k_kit_vote(DevTables t, const int32_t *__restrict__ wlen, long l
     if (i5 < 0) i5 += n_subset;
     if (i3 < 0) i3 += n_subset;
     vote[r] = subset[(s5 > s3) ? i5 : i3];
+}
+
+// get_most_abundant_kits per CLI batch (scanner_base.py:657-678, :714-722): one CTA per batch of `batch_size` reads.
+// The kit named by most votes wins; among kits with the same count the one seen first in the batch (the reference
+// counts in a dict -- insertion order -- and sorts stably by count).
+constexpr int kMaxKits = 256;
+
+__global__ void k_batch_kit(const int32_t *__restrict__ vote, long long n_reads, int batch_size,
+                            const int32_t *__restrict__ kit_of_layout, int n_kits, int32_t *__restrict__ batch_kit)
+{
+    __shared__ unsigned cnt[kMaxKits], first[kMaxKits];
+    for (int k = threadIdx.x; k < n_kits; k += blockDim.x) { cnt[k] = 0; first[k] = 0xffffffffu; }
+    __syncthreads();
+    const long long lo = (long long)blockIdx.x * batch_size, hi = min(n_reads, lo + (long long)batch_size);
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const int k = kit_of_layout[vote[i]];
+        atomicAdd(&cnt[k], 1u);
+        atomicMin(&first[k], (unsigned)(i - lo));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = -1;
+        for (int k = 0; k < n_kits; ++k)
+            if (cnt[k] > 0 && (best < 0 || cnt[k] > cnt[best] || (cnt[k] == cnt[best] && first[k] < first[best]))) best = k;
+        batch_kit[blockIdx.x] = best;
+    }
 }
 
 __global__ void k_histogram(const qcb_result *__restrict__ res, long long n_reads,

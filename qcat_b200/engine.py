@@ -126,6 +126,25 @@ class DevicePlan(object):
                                         _vp(sub) if sub is not None else None, nsub, _vp(out)))
         return out
 
+    def detect_auto(self, win5, tail3, wlen, read_len, kit_of_layout, batch_size, out=None, return_kits=False):
+        """qcb_detect_auto on host numpy arrays: one pass over all layouts, per-batch kit vote on the device, detection
+        restricted to every batch's kit.  kit_of_layout: Tables.kit_index()[1]."""
+        win5 = np.ascontiguousarray(win5, dtype=np.uint8)
+        tail3 = np.ascontiguousarray(tail3, dtype=np.uint8)
+        wlen = np.ascontiguousarray(wlen, dtype=np.int32)
+        read_len = np.ascontiguousarray(read_len, dtype=np.int64)
+        kits = np.ascontiguousarray(kit_of_layout, dtype=np.int32)
+        if kits.size != self.tables.n_layouts:
+            raise ValueError("kit_of_layout needs one entry per layout")
+        n = int(wlen.shape[0])
+        stride = int(win5.shape[1]) if win5.ndim == 2 else int(win5.size // max(n, 1))
+        if out is None:
+            out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+        batch_kit = np.zeros(max(1, (n + int(batch_size) - 1) // max(int(batch_size), 1)), dtype=np.int32)
+        _ffi.check(self._lib.qcb_detect_auto(self._handle, _vp(win5), _vp(tail3), stride, _vp(wlen), _vp(read_len), n,
+                                             _vp(kits), int(batch_size), _vp(out), _vp(batch_kit)))
+        return (out, batch_kit) if return_kits else out
+
     def detect_reads(self, read_sequences, subset=None):
         win5, tail3, wlen, read_len, _ = pack_windows(read_sequences, self.tables.max_align_length)
         return self.detect(win5, tail3, wlen, read_len, subset)
@@ -165,6 +184,14 @@ class DevicePlan(object):
                                                ctypes.c_void_p(d_wlen), ctypes.c_void_p(d_read_len), int(n_reads),
                                                _vp(sub) if sub is not None else None, nsub,
                                                ctypes.c_void_p(d_out), ctypes.c_void_p(stream)))
+
+    def detect_auto_device(self, d_win5, d_tail3, stride, d_wlen, d_read_len, n_reads, kit_of_layout, batch_size, d_out,
+                           d_batch_kit=0, stream=0):
+        kits = np.ascontiguousarray(kit_of_layout, dtype=np.int32)
+        _ffi.check(self._lib.qcb_detect_auto_device(self._handle, ctypes.c_void_p(d_win5), ctypes.c_void_p(d_tail3), int(stride),
+                                                    ctypes.c_void_p(d_wlen), ctypes.c_void_p(d_read_len), int(n_reads),
+                                                    _vp(kits), int(batch_size), ctypes.c_void_p(d_out),
+                                                    ctypes.c_void_p(d_batch_kit) if d_batch_kit else None, ctypes.c_void_p(stream)))
 
     def kit_vote_device(self, d_win5, d_tail3, stride, d_wlen, n_reads, d_vote, stream=0):
         _ffi.check(self._lib.qcb_kit_vote_device(self._handle, ctypes.c_void_p(d_win5), ctypes.c_void_p(d_tail3), int(stride),

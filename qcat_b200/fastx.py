@@ -257,6 +257,9 @@ def _score_chunk(scanner, plan, packed, batch_size, nobatch, chunk=None, qcat_co
     if nobatch or len(kit_names) == 1:
         # no vote needed (single-read mode, or every layout names the same kit): one device call per chunk
         plan.detect(win5, tail3, wlen, read_len, scanner._subset_for(plan, scanner.layouts), out=results)
+    elif tables.kit_index()[1] is not None and hasattr(plan, "detect_auto"):
+        # one pass (qcb_detect_auto): adapter stage over all layouts once, per-batch vote and kit restriction on the device
+        plan.detect_auto(win5, tail3, wlen, read_len, tables.kit_index()[1], batch_size, out=results)
     else:
         vote = plan.kit_vote(win5, tail3, wlen)                 # one device call for the whole chunk
         kit_of_layout = np.array([kit_names.index(k) for k in names], dtype=np.int64)

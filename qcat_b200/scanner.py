@@ -277,21 +277,30 @@ class GpuScannerMixin(object):
         packed_all = pack_windows(read_sequences, qcat_config.max_align_length)[:4]
 
         names = [layout.kit for layout in self.layouts]
+        kit_names, kit_of_layout = plan.tables.kit_index()
+        records = None
         if not read_sequences:
             kit_name = None
         elif len(set(names)) == 1:
             kit_name = names[0]
+        elif kit_of_layout is not None and hasattr(plan, "detect_auto"):
+            # one pass: adapter stage over all layouts, the whole call votes as one batch on the device, detection
+            # continues on the voted kit's layouts (qcb_detect_auto).  Every read votes, also those beyond n_out.
+            records, batch_kit = plan.detect_auto(*packed_all, kit_of_layout, len(read_sequences), return_kits=True)
+            kit_name = kit_names[int(batch_kit[0])]
+            records = records[:n_out]
         else:
             kit_name = self._kit_from_votes(plan.kit_vote(packed_all[0], packed_all[1], packed_all[2]), names)
 
         results = []
         if n_out:
-            self.override_kit_name = kit_name
-            try:
-                packed = tuple(a[:n_out] for a in packed_all)
-                records = self._detect_records(plan, packed, self._kits())
-            finally:
-                self.override_kit_name = None
+            if records is None:
+                self.override_kit_name = kit_name
+                try:
+                    packed = tuple(a[:n_out] for a in packed_all)
+                    records = self._detect_records(plan, packed, self._kits())
+                finally:
+                    self.override_kit_name = None
             results = self._records_to_dicts(plan, records)
             if self.scan_middle_adapter:
                 self.override_kit_name = kit_name

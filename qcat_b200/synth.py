@@ -63,7 +63,7 @@ def _filled(layout, b1, b2=None):
 
 def generate(layouts, n_reads, seed, W=150, stride=160, foreign_layouts=(), sub=0.08, dele=0.06, ins=0.05,
              p_none=0.10, p_foreign=0.02, p5=0.95, p3=0.70, p_conflict=0.01, p_n=0.001, mean_len=8000.0,
-             min_len=300, max_len=50000):
+             min_len=300, max_len=50000, length_model="lognormal"):
     """Returns dict(win5, tail3, wlen, read_len, truth_barcode, truth_layout5, truth_layout3)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n = int(n_reads)
@@ -151,9 +151,14 @@ def generate(layouts, n_reads, seed, W=150, stride=160, foreign_layouts=(), sub=
     for w in (win5, tail3):
         w[rng.random(w.shape, dtype=np.float32) < p_n] = ord("N")
 
-    sigma = 0.9
-    mu = np.log(mean_len) - 0.5 * sigma * sigma
-    read_len = np.clip(rng.lognormal(mu, sigma, size=n), max(min_len, 2 * W), max_len).astype(np.int64)
+    if length_model == "loguniform":          # "mixed lengths": every octave of [min_len, max_len] equally likely
+        lo = float(max(min_len, 2 * W))
+        read_len = np.floor(lo * np.exp(rng.random(n) * np.log(float(max_len) / lo))).astype(np.int64)
+        read_len = np.clip(read_len, int(lo), max_len)
+    else:
+        sigma = 0.9
+        mu = np.log(mean_len) - 0.5 * sigma * sigma
+        read_len = np.clip(rng.lognormal(mu, sigma, size=n), max(min_len, 2 * W), max_len).astype(np.int64)
 
     out5 = np.zeros((n, stride), dtype=np.uint8)
     out3 = np.zeros((n, stride), dtype=np.uint8)
@@ -177,3 +182,35 @@ def windows_to_reads(data, indices=None):
         tail = bytes(data["tail3"][i, :W]).decode("latin-1")
         reads.append(head + "A" * (n - 2 * W) + tail if n >= 2 * W else (head + tail)[:max(n, W)])
     return reads
+
+
+_PARALLEL_JOB = None
+
+
+def _parallel_chunk(index):
+    layouts, chunk, seed, kwargs, n_total = _PARALLEL_JOB
+    lo = index * chunk
+    base = [int(v) for v in np.atleast_1d(seed)]
+    return generate(layouts, min(chunk, n_total - lo), seed=base + [int(index)], **kwargs)
+
+
+def generate_parallel(layouts, n_reads, seed, workers=None, chunk=65536, **kwargs):
+    """`generate` for large batches: the reads are drawn in chunks of `chunk` reads, chunk c from the generator seeded
+    with (seed, c), by a pool of forked worker processes -- the result depends on (seed, chunk) only, not on the worker
+    count.  Fork-based: call it before the process initialises CUDA (workers only run numpy)."""
+    import multiprocessing
+    import os
+    global _PARALLEL_JOB
+    n = int(n_reads)
+    n_chunks = max(1, (n + chunk - 1) // chunk)
+    workers = max(1, min(n_chunks, int(workers or os.cpu_count() or 1)))
+    _PARALLEL_JOB = (list(layouts), int(chunk), seed, kwargs, n)
+    try:
+        if workers == 1:
+            parts = [_parallel_chunk(i) for i in range(n_chunks)]
+        else:
+            with multiprocessing.get_context("fork").Pool(workers) as pool:
+                parts = pool.map(_parallel_chunk, range(n_chunks))
+    finally:
+        _PARALLEL_JOB = None
+    return {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts], axis=0)) for k in parts[0]}

@@ -107,6 +107,15 @@ class Tables(object):
         wanted = kit_name.lower()
         return [i for i, name in enumerate(self.kit_names) if name.lower() == wanted]
 
+    def kit_index(self):
+        """(kit names in first-seen order, int32 kit index per layout) -- the `kit_of_layout` table of qcb_detect_auto.
+        Returns (names, None) when two kit names differ only by case: the reference counts votes per exact name but
+        selects layouts case-insensitively (scanner_base.py:606-611), which one table cannot express."""
+        names = list(dict.fromkeys(self.kit_names))
+        if len(set(n.lower() for n in names)) != len(names):
+            return names, None
+        return names, np.array([names.index(k) for k in self.kit_names], dtype=np.int32)
+
     def group_size(self, layout_index, k):
         g = int(self.group[layout_index * 2 + k])
         return 0 if g < 0 else int(self.group_off[g + 1] - self.group_off[g])

@@ -95,7 +95,8 @@ def encode(scanner, result):
             int(result["trim3p"]), int(result["exit_status"]))
 
 
-def main():
+def build_reads():
+    """The golden read set (fixtures, test literals, adversarial reads) and the index range of every part."""
     rng = random.Random(20261017)
     reads = []
     ranges = {}
@@ -109,6 +110,18 @@ def main():
     adv = adversarial_reads(rng)
     ranges["adversarial"] = (len(reads), len(reads) + len(adv))
     reads += adv
+    return reads, ranges
+
+
+def small_subset(ranges):
+    return ([i for i in range(ranges["barcode_1k.fastq"][0], ranges["barcode_1k.fastq"][0] + 250)] +
+            [i for i in range(ranges["nobarcode_1k.fastq"][0], ranges["nobarcode_1k.fastq"][0] + 250)] +
+            [i for name in FIXTURES[2:] for i in range(*ranges[name])] +
+            list(range(*ranges["literals"])) + list(range(*ranges["adversarial"])))
+
+
+def main():
+    reads, ranges = build_reads()
     print("reads:", len(reads), ranges)
 
     cfg = ref_config.qcatConfig()
@@ -134,10 +147,7 @@ def main():
 
     everything = list(range(len(reads)))
     fixture_all = [i for name in FIXTURES for i in range(*ranges[name])]
-    small = ([i for i in range(ranges["barcode_1k.fastq"][0], ranges["barcode_1k.fastq"][0] + 250)] +
-             [i for i in range(ranges["nobarcode_1k.fastq"][0], ranges["nobarcode_1k.fastq"][0] + 250)] +
-             [i for name in FIXTURES[2:] for i in range(*ranges[name])] +
-             list(range(*ranges["literals"])) + list(range(*ranges["adversarial"])))
+    small = small_subset(ranges)
 
     add_case("auto/single/all", "epi2me", None, False, everything)
     for kit in ("PBK004/LWB001", "RBK001", "RBK004", "NBD103/NBD104", "NBD104/NBD114", "RAB204/RAB214", "PBC096",

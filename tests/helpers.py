@@ -83,6 +83,24 @@ def oracle_kit_vote(tables, win5, tail3, wlen, threads=None):
     return vote
 
 
+def oracle_detect_auto(tables, win5, tail3, wlen, read_len, batch_size=4000, threads=None, return_kits=False):
+    """CPU oracle of the auto-kit flow (detect_barcode_batch, scanner_base.py:714-733): per batch of `batch_size` reads
+    the kit vote over all layouts (qo_kit_vote + get_most_abundant_kits), then qo_detect restricted to that kit."""
+    n = int(len(wlen))
+    names = list(tables.kit_names)
+    kit_names = list(dict.fromkeys(names))
+    out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+    kits = []
+    vote = oracle_kit_vote(tables, win5, tail3, wlen, threads=threads)
+    for lo in range(0, n, batch_size):
+        hi = min(n, lo + batch_size)
+        kit = kit_from_votes(vote[lo:hi], names)
+        kits.append(kit_names.index(kit))
+        out[lo:hi] = oracle_detect(tables, win5[lo:hi], tail3[lo:hi], wlen[lo:hi], read_len[lo:hi],
+                                   subset=tables.kit_subset(kit), threads=threads)
+    return (out, np.asarray(kits, dtype=np.int32)) if return_kits else out
+
+
 def oracle_count_cells(tables, win5, tail3, wlen, subset=None):
     lib = oracle_lib()
     st, keep = _ffi.tables_struct(tables)
@@ -166,3 +184,12 @@ class OraclePlan(object):
     def scan_windows(self, windows, subset=None):
         self.calls += 1
         return oracle_scan(self.tables, windows, subset)
+
+    def detect_auto(self, win5, tail3, wlen, read_len, kit_of_layout, batch_size, out=None, return_kits=False):
+        self.calls += 1
+        assert list(kit_of_layout) == list(self.tables.kit_index()[1])
+        got, kits = oracle_detect_auto(self.tables, win5, tail3, wlen, read_len, batch_size=int(batch_size), return_kits=True)
+        if out is not None:
+            out[...] = got
+            got = out
+        return (got, kits) if return_kits else got

@@ -1,8 +1,12 @@
-"""GPU, BASELINE-size batches (1 M reads): size-independent properties of the CUDA path.
+"""GPU, BASELINE-size batches (1 M reads): bit-identity with the CPU oracle on every read, plus size-independent
+properties of the CUDA path.
 
-The oracle is too slow to check a million reads, so at full size the checks are: the packed kernels agree with
-the independent generic kernels on every record; a random 20 k subset agrees with the CPU oracle; results do not
-depend on batch order or chunk boundaries; the device histogram accounts for every read."""
+The 1 M-read batch is drawn (with repetition) from 250 000 distinct synthetic reads plus 5 000 ragged ones, so the
+oracle only has to score the distinct reads (~25 s on the box's cores) for all one million records to be compared.
+Further checks: the packed kernels agree with the independent generic kernels on every record; results do not depend
+on batch order or chunk boundaries; the device histogram accounts for every read."""
+import os
+
 import numpy as np
 import pytest
 
@@ -35,6 +39,7 @@ def full_batch():
     tables = Tables(sc.layouts, config.qcatConfig(), "epi2me", sc.min_quality)
     plan = engine.DevicePlan(tables, device=0)
     result = plan.detect(data["win5"], data["tail3"], data["wlen"], data["read_len"])
+    data["unique"], data["pick"], data["short"] = unique, pick, np.unique(short)
     yield data, tables, plan, result
     plan.close()
 
@@ -50,11 +55,15 @@ def test_packed_and_generic_kernels_agree_on_a_million_reads(full_batch):
     assert 0.5 < called < 0.95
 
 
-def test_random_subset_matches_oracle(full_batch):
+def test_every_read_of_the_million_matches_oracle(full_batch):
+    """bit-identical records on 1 M synthetic reads of the headline config.  The oracle scores the
+    250 000 distinct reads and the ragged ones; every one of the 1 M device records is compared with its read's."""
     data, tables, plan, fast = full_batch
-    idx = np.sort(np.random.default_rng(5).choice(N_FULL, size=20000, replace=False))
-    want = helpers.oracle_detect(tables, data["win5"][idx], data["tail3"][idx], data["wlen"][idx], data["read_len"][idx])
-    helpers.assert_records_equal(fast[idx], want, "1M batch, 20k subset vs oracle")
+    u = data["unique"]
+    want = helpers.oracle_detect(tables, u["win5"], u["tail3"], u["wlen"], u["read_len"])[data["pick"]]
+    idx = data["short"]
+    want[idx] = helpers.oracle_detect(tables, data["win5"][idx], data["tail3"][idx], data["wlen"][idx], data["read_len"][idx])
+    helpers.assert_records_equal(fast, want, "1M batch, every record vs oracle")
 
 
 def test_order_and_chunking_invariance(full_batch):
@@ -85,18 +94,29 @@ def test_device_histogram_accounts_for_every_read(full_batch):
     assert hist["none"] == int((fast["barcode"] < 0).sum()) and len(hist) >= 90
 
 
-def test_dual_and_small_kits_at_scale():
-    """configs[1] (12 barcodes) and configs[3] (dual 24 x 96): packed == generic on 200 k reads each."""
+NBD196_FOLDER = os.path.join(helpers.ROOT, "qcat_b200", "resources", "nbd196")
+
+
+@pytest.mark.parametrize("mode,kit,kit_folder,n", [("epi2me", "NBD103/NBD104", None, 200000), ("dual", None, None, 200000),
+                                                   ("epi2me", "NBD196", NBD196_FOLDER, 100000)])
+def test_other_configs_at_scale_match_oracle(mode, kit, kit_folder, n):
+    """configs[1] (12 barcodes), configs[3] (dual 24 x 96) and the synthetic EXP-NBD196 kit: every record of 100-200 k
+    reads equals the CPU oracle's, and the packed kernels equal the generic ones."""
     from qcat_b200 import config, engine, scanner, synth
     from qcat_b200.tables import Tables
-    for cls, kit, mode in ((scanner.BarcodeScannerEPI2ME, "NBD103/NBD104", "epi2me"), (scanner.BarcodeScannerDual, None, "dual")):
-        sc = cls(kit=kit)
-        data = synth.generate(sc.layouts, 200000, seed=77)
-        tables = Tables(sc.layouts, config.qcatConfig(), mode, sc.min_quality)
-        plan = engine.DevicePlan(tables, device=0)
+    cls = scanner.BarcodeScannerDual if mode == "dual" else scanner.BarcodeScannerEPI2ME
+    sc = cls(kit=kit, kit_folder=kit_folder)
+    data = synth.generate(sc.layouts, n, seed=77)
+    tables = Tables(sc.layouts, config.qcatConfig(), mode, sc.min_quality)
+    plan = engine.DevicePlan(tables, device=0)
+    try:
         fast = plan.detect(data["win5"], data["tail3"], data["wlen"], data["read_len"])
+        assert plan.info()["fast_adapter"] == 1 and plan.info()["fast_barcode"] == 1
         plan.set_force_generic(True)
         generic = plan.detect(data["win5"], data["tail3"], data["wlen"], data["read_len"])
-        helpers.assert_records_equal(fast, generic, "packed vs generic, %s" % mode)
+        helpers.assert_records_equal(fast, generic, "packed vs generic, %s %s" % (mode, kit))
+        want = helpers.oracle_detect(tables, data["win5"], data["tail3"], data["wlen"], data["read_len"])
+        helpers.assert_records_equal(fast, want, "%d reads vs oracle, %s %s" % (n, mode, kit))
         assert (fast["barcode"] >= 0).mean() > 0.3
+    finally:
         plan.close()
