@@ -6,6 +6,8 @@
  *   - the in-process FFI the reference itself uses: parasail-python (ctypes) ->
  *     parasail_sg_striped_32(s1, s1Len, s2, s2Len, open, gap, matrix) called at
  *     qcat/scanner_base.py:111-117 (barcodes) and :214-218 (adapters)      -> qcb_sg_batch()
+ *     and parasail_sg_stats_striped_32 (:106-123, :168-172)                 -> qcb_sg_stats_batch()
+ *   - BarcodeScannerSimple.scan (scanner_simple.py:47-92)                   -> qcb_detect*() / qcb_scan() on a QCB_MODE_SIMPLE plan
  *   - the Python loops around it: find_best_adapter_template (scanner_base.py:313-359),
  *     extract_barcode_region (:29-60), find_highest_scoring_barcode (:63-141),
  *     BarcodeScannerEPI2ME.scan (scanner_epi2me.py:33-144), BarcodeScannerDual.scan
@@ -36,6 +38,7 @@ extern "C" {
 
 #define QCB_MODE_EPI2ME 0
 #define QCB_MODE_DUAL 1
+#define QCB_MODE_SIMPLE 2   /* scanner_simple.py: template group 0 = the bare barcodes, one placeholder layout, no adapter stage */
 
 /* Flattened scanner description (built by qcat_b200/tables.py).  All pointers are host pointers and are
  * copied by qcb_plan_create(). */
@@ -75,7 +78,7 @@ typedef struct {
 
 /* One record per read == build_return_dict (scanner_base.py:362-390).  32 bytes. */
 typedef struct {
-    int32_t layout;         /* index of result['adapter'] in the tables' layouts, -1 = None */
+    int32_t layout;         /* index of result['adapter'] in the tables' layouts, -1 = None (always in simple mode) */
     int32_t barcode;        /* index inside the layout's template group, -1 = None; dual: idx1 * n2 + idx2 */
     double  barcode_score;
     int32_t adapter_end;
@@ -119,13 +122,26 @@ int       qcb_plan_set_profiling(qcb_plan *plan, int enable);
 int       qcb_plan_stage_times(qcb_plan *plan, double *ms, int64_t *launches, int reset);
 
 /* Batched semi-global alignment, every query against every reference: out[q * n_refs + r].
- * Replaces parasail.sg_striped_32 (scanner_base.py:111-117, 214-218).  Host buffers. */
+ * The semantics of parasail.sg_striped_32 (scanner_base.py:111-117, 214-218) as a stand-alone call -- a parity-test
+ * primitive: host buffers, device memory allocated and released per call, default stream.  The production path never
+ * aligns one pair at a time; it runs the batched pipeline of qcb_detect*(). */
 int qcb_sg_batch(int device,
                  const uint8_t *queries, const int32_t *query_off, int32_t n_queries,
                  const uint8_t *refs, const int32_t *ref_off, int32_t n_refs,
                  int32_t open, int32_t extend,
                  const int32_t *matrix, int32_t msize, const uint8_t *mapper,
                  int32_t *score, int32_t *end_query, int32_t *end_ref);
+
+/* The same with the alignment statistics of parasail.sg_stats_striped_32 (scanner_base.py:20-26; simple scanner
+ * :106-123, align_adapter_identity :168-172): matches, similar (positive-scoring columns) and length.  Which of several
+ * equal-scoring alignments is counted follows parasail's recurrence as restated in oracle/qcat_oracle.c (unpinned). */
+int qcb_sg_stats_batch(int device,
+                       const uint8_t *queries, const int32_t *query_off, int32_t n_queries,
+                       const uint8_t *refs, const int32_t *ref_off, int32_t n_refs,
+                       int32_t open, int32_t extend,
+                       const int32_t *matrix, int32_t msize, const uint8_t *mapper,
+                       int32_t *score, int32_t *end_query, int32_t *end_ref,
+                       int32_t *matches, int32_t *similar, int32_t *length);
 
 /* detect_barcode for n_reads reads given as their two windows (see qcat_b200/tables.py:pack_windows):
  * win5[i] = read[:W], tail3[i] = read[-W:] (not reverse-complemented), slots of `stride` bytes

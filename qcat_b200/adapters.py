@@ -71,3 +71,40 @@ def populate_adapter_layouts(folder=None):
         return _bundled_layouts()
     filenames = glob.glob(os.path.join(folder, "*.yml")) if os.path.isdir(folder) else [folder]
     return [layout for layout in (read_adapter_layout(f) for f in filenames) if layout]
+
+
+def _simple_fasta(handle):
+    """(title, sequence) pairs with Bio's SimpleFastaParser semantics (what the reference parses barcode files with)."""
+    title, chunks = None, []
+    for line in handle:
+        if line.startswith(">"):
+            if title is not None:
+                yield title, "".join(chunks).replace(" ", "").replace("\r", "")
+            title, chunks = line[1:].rstrip(), []
+        elif title is not None:
+            chunks.append(line.rstrip())
+    if title is not None:
+        yield title, "".join(chunks).replace(" ", "").replace("\r", "")
+
+
+def get_barcodes_from_fastq(reads_fa):
+    """Barcodes of a FASTA file, ids 1.. in file order (reference adapters.py:108-118; the name says fastq)."""
+    with open(reads_fa) as handle:
+        barcodes = [read_barcode({"name": title, "id": i + 1, "sequence": seq}) for i, (title, seq) in enumerate(_simple_fasta(handle))]
+    if not barcodes:
+        logging.error("Couldn't find barcodes in {}".format(reads_fa))
+    return barcodes
+
+
+def get_barcodes_simple(kit="standard", filename=None):
+    """barcode_set_1 of simple_<kit>.yml (reference adapters.py:121-135): `standard` = 24, `extended` = 96 + 24 barcodes."""
+    if filename and os.path.isfile(filename):
+        import yaml
+        with open(filename, "r") as stream:
+            return read_barcode_set(yaml.load(stream, Loader=yaml.FullLoader).get("barcode_set_1", []))
+    wanted = "simple_{}.yml".format(kit)
+    with open(KIT_JSON, "r") as stream:
+        for entry in json.load(stream)["kits"]:
+            if entry.get("file") == wanted:
+                return read_barcode_set(entry.get("barcode_set_1", []))
+    raise IOError("[Errno 2] No such file or directory: '{}'".format(wanted))

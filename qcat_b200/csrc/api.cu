@@ -70,6 +70,7 @@ struct qcb_plan {
     FastPlan fast;                   // packed-kernel tables (kernels_fast.cuh)
     // workspace, sized per chunk of reads
     DeviceBuffer wins, codes, ad_score, ad_end, sel, bc_score, subset_dev, misc, long_part, long_row;
+    DeviceBuffer bc_endq;                           // simple mode: end_query per (window, barcode)
     DeviceBuffer auto_vote, auto_kit, auto_map;   // auto-kit flow: per-read vote, per-batch kit, layout -> kit table
     int long_ov = 0;                 // warm-up rows of k_adapter_long (0 = chunking not provably exact for these tables)
     cudaStream_t stream = nullptr;   // kernels of the host-buffer entry points
@@ -179,7 +180,9 @@ int validate_tables(const qcb_tables *h)
     if (h->amat_size <= 0 || h->amat_size > kMaxMatrix || h->bmat_size <= 0 || h->bmat_size > kMaxMatrix)
         return fail("substitution matrix size must be in [1, %d]", kMaxMatrix);
     if (h->max_align_length <= 0) return fail("max_align_length must be positive");
-    if (h->mode != QCB_MODE_EPI2ME && h->mode != QCB_MODE_DUAL) return fail("unknown mode %d", h->mode);
+    if (h->mode != QCB_MODE_EPI2ME && h->mode != QCB_MODE_DUAL && h->mode != QCB_MODE_SIMPLE) return fail("unknown mode %d", h->mode);
+    if (h->mode == QCB_MODE_SIMPLE && (h->n_layouts != 1 || h->n_groups < 1 || h->group[0] != 0))
+        return fail("simple mode needs one placeholder layout whose barcode set is template group 0");
     for (int L = 0; L < h->n_layouts; ++L) {
         int alen = h->adapter_off[L + 1] - h->adapter_off[L];
         if (alen <= 0 || alen > kMaxTemplate) return fail("adapter %d length %d outside [1, %d]", L, alen, kMaxTemplate);
@@ -234,6 +237,39 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
     const long long nw = window_mode ? n : 2 * n;
     const DevTables &t = p->t;
     const int bslots = p->bmax0 + (t.mode == QCB_MODE_DUAL ? p->bmax1 : 0);
+    if (t.mode == QCB_MODE_SIMPLE) {
+        // scanner_simple.py:47-92: no adapter stage; every bare barcode against the whole window (generic int32 kernel,
+        // which also returns the end_query the simple scanner reports as adapter_end)
+        if (d_vote || autokit) return fail("the simple scanner has no kit vote");
+        const uint8_t *wins = d_win5;
+        if (!window_mode) {
+            StageTimer timer(p, 0, st);
+            if (p->wins.reserve((size_t)nw * stride)) return 1;
+            k_orient<<<grid_for(nw * stride, 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, (uint8_t *)p->wins.ptr);
+            p->launches++;
+            wins = (const uint8_t *)p->wins.ptr;
+        }
+        if (p->sel.reserve((size_t)nw * sizeof(WindowSel)) || p->bc_score.reserve((size_t)nw * bslots * 4) ||
+            p->bc_endq.reserve((size_t)nw * bslots * 4)) return 1;
+        WindowSel *sel = (WindowSel *)p->sel.ptr;
+        int32_t *bc_score = (int32_t *)p->bc_score.ptr, *bc_endq = (int32_t *)p->bc_endq.ptr;
+        {
+            StageTimer timer(p, 2, st);
+            k_select_simple<<<grid_for(nw, 256), 256, 0, st>>>(d_wlen, wshift, nw, sel);
+            p->launches++;
+        }
+        {
+            StageTimer timer(p, 3, st);
+            k_barcode_generic<<<grid_for(nw * bslots, 128), 128, 0, st>>>(t, wins, stride, nw, sel, p->bmax0, bslots, bc_score, bc_endq);
+            p->launches++;
+        }
+        StageTimer timer(p, 4, st);
+        if (window_mode) k_scan_out<<<grid_for(nw, 128), 128, 0, st>>>(t, d_wlen, nw, sel, bc_score, p->bmax0, bslots, d_out, bc_endq);
+        else k_finalize<<<grid_for(n, 128), 128, 0, st>>>(t, d_wlen, d_read_len, n, sel, bc_score, p->bmax0, bslots, d_out, bc_endq);
+        p->launches++;
+        QCB_CUDA(cudaGetLastError());
+        return 0;
+    }
     // the ASCII copy of the oriented windows is only read by the generic kernels
     const bool packed_only = !p->force_generic && !window_mode && p->fast.adapter_ok && p->fast.barcode_ok &&
                              stride <= kFastMaxStride && (stride % 16) == 0 && n_subset <= 64;
@@ -323,13 +359,13 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
         int rc = fast_barcode_stage(p->fast, t, nw, p->bmax0, bslots, bc_score, st, &p->launches);
         if (rc) return fail("fast barcode stage launch failed");
     } else {
-        k_barcode_generic<<<grid_for(nw * bslots, 128), 128, 0, st>>>(t, wins, stride, nw, sel, p->bmax0, bslots, bc_score);
+        k_barcode_generic<<<grid_for(nw * bslots, 128), 128, 0, st>>>(t, wins, stride, nw, sel, p->bmax0, bslots, bc_score, nullptr);
         p->launches++;
     }
     }
     StageTimer timer(p, 4, st);
-    if (window_mode) k_scan_out<<<grid_for(nw, 128), 128, 0, st>>>(t, d_wlen, nw, sel, bc_score, p->bmax0, bslots, d_out);
-    else k_finalize<<<grid_for(n, 128), 128, 0, st>>>(t, d_wlen, d_read_len, n, sel, bc_score, p->bmax0, bslots, d_out);
+    if (window_mode) k_scan_out<<<grid_for(nw, 128), 128, 0, st>>>(t, d_wlen, nw, sel, bc_score, p->bmax0, bslots, d_out, nullptr);
+    else k_finalize<<<grid_for(n, 128), 128, 0, st>>>(t, d_wlen, d_read_len, n, sel, bc_score, p->bmax0, bslots, d_out, nullptr);
     p->launches++;
     QCB_CUDA(cudaGetLastError());
     return 0;
@@ -562,7 +598,7 @@ void qcb_plan_destroy(qcb_plan *p)
     fast_plan_free(p->fast);
     p->wins.release(); p->codes.release(); p->ad_score.release(); p->ad_end.release(); p->sel.release(); p->bc_score.release();
     p->subset_dev.release(); p->misc.release(); p->long_part.release(); p->long_row.release();
-    p->auto_vote.release(); p->auto_kit.release(); p->auto_map.release();
+    p->auto_vote.release(); p->auto_kit.release(); p->auto_map.release(); p->bc_endq.release();
     if (p->slab) cudaFree(p->slab);
     for (int i = 0; i < 2; ++i) {
         p->in_stage2[i].release(); p->out_stage2[i].release();
@@ -626,15 +662,16 @@ int qcb_plan_stage_times(qcb_plan *p, double *ms, int64_t *launches, int reset)
     return 0;
 }
 
-int qcb_sg_batch(int device, const uint8_t *queries, const int32_t *query_off, int32_t n_queries,
-                 const uint8_t *refs, const int32_t *ref_off, int32_t n_refs, int32_t open, int32_t extend,
-                 const int32_t *matrix, int32_t msize, const uint8_t *mapper,
-                 int32_t *score, int32_t *end_query, int32_t *end_ref)
+// Shared body of qcb_sg_batch / qcb_sg_stats_batch: a parity-test primitive (everything is allocated and released per
+// call; the production path never goes through here).  n_out = 3 (score, end_query, end_ref) or 6 (+ statistics).
+static int sg_batch_impl(int device, const uint8_t *queries, const int32_t *query_off, int32_t n_queries,
+                         const uint8_t *refs, const int32_t *ref_off, int32_t n_refs, int32_t open, int32_t extend,
+                         const int32_t *matrix, int32_t msize, const uint8_t *mapper, int32_t *const *outs, int n_out)
 {
     if (n_queries < 0 || n_refs < 0) return fail("negative count");
     if (n_queries == 0 || n_refs == 0) return 0;
-    if (!queries || !query_off || !refs || !ref_off || !matrix || !mapper || !score || !end_query || !end_ref)
-        return fail("NULL buffer");
+    if (!queries || !query_off || !refs || !ref_off || !matrix || !mapper) return fail("NULL buffer");
+    for (int i = 0; i < n_out; ++i) if (!outs[i]) return fail("NULL buffer");
     if (msize <= 0 || msize > kMaxMatrix) return fail("matrix size must be in [1, %d]", kMaxMatrix);
     for (int i = 0; i < 256; ++i) if (mapper[i] >= msize) return fail("mapper entry %d out of range", i);
     for (int r = 0; r < n_refs; ++r) {
@@ -645,30 +682,56 @@ int qcb_sg_batch(int device, const uint8_t *queries, const int32_t *query_off, i
     if (ndev <= 0) return fail("no CUDA device available (libqcat_b200 has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail("device %d out of range", device);
     QCB_CUDA(cudaSetDevice(device));
-    size_t qb = (size_t)query_off[n_queries], rb = (size_t)ref_off[n_refs];
-    size_t pairs = (size_t)n_queries * n_refs;
-    uint8_t *d_q = nullptr, *d_r = nullptr, *d_map = nullptr;
-    int32_t *d_qo = nullptr, *d_ro = nullptr, *d_mat = nullptr, *d_out = nullptr;
+    const size_t qb = (size_t)query_off[n_queries], rb = (size_t)ref_off[n_refs];
+    const size_t pairs = (size_t)n_queries * n_refs;
+    // one device slab: queries | refs | mapper | query offsets | ref offsets | matrix | outputs
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t o_q = 0, o_r = up(qb + 16), o_map = o_r + up(rb + 16), o_qo = o_map + 256;
+    const size_t o_ro = o_qo + up((size_t)(n_queries + 1) * 4), o_mat = o_ro + up((size_t)(n_refs + 1) * 4);
+    const size_t o_out = o_mat + up((size_t)msize * msize * 4), total = o_out + pairs * 4 * n_out;
+    uint8_t *d = nullptr;
+    QCB_CUDA(cudaMalloc(&d, total));
     int rc = 0;
-    auto cleanup = [&]() { cudaFree(d_q); cudaFree(d_r); cudaFree(d_map); cudaFree(d_qo); cudaFree(d_ro); cudaFree(d_mat); cudaFree(d_out); };
-#define SG_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail("%s failed: %s", #call, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
-    SG_CUDA(cudaMalloc(&d_q, qb + 16)); SG_CUDA(cudaMalloc(&d_r, rb + 16)); SG_CUDA(cudaMalloc(&d_map, 256));
-    SG_CUDA(cudaMalloc(&d_qo, (size_t)(n_queries + 1) * 4)); SG_CUDA(cudaMalloc(&d_ro, (size_t)(n_refs + 1) * 4));
-    SG_CUDA(cudaMalloc(&d_mat, (size_t)msize * msize * 4)); SG_CUDA(cudaMalloc(&d_out, pairs * 12));
-    SG_CUDA(cudaMemcpy(d_q, queries, qb, cudaMemcpyHostToDevice)); SG_CUDA(cudaMemcpy(d_r, refs, rb, cudaMemcpyHostToDevice));
-    SG_CUDA(cudaMemcpy(d_map, mapper, 256, cudaMemcpyHostToDevice));
-    SG_CUDA(cudaMemcpy(d_qo, query_off, (size_t)(n_queries + 1) * 4, cudaMemcpyHostToDevice));
-    SG_CUDA(cudaMemcpy(d_ro, ref_off, (size_t)(n_refs + 1) * 4, cudaMemcpyHostToDevice));
-    SG_CUDA(cudaMemcpy(d_mat, matrix, (size_t)msize * msize * 4, cudaMemcpyHostToDevice));
-    k_sg_batch<<<grid_for((long long)pairs, 128), 128>>>(d_q, d_qo, n_queries, d_r, d_ro, n_refs, open, extend, d_mat, msize, d_map,
-                                                        d_out, d_out + pairs, d_out + 2 * pairs);
+#define SG_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail("%s failed: %s", #call, cudaGetErrorString(e_)); cudaFree(d); return rc; } } while (0)
+    SG_CUDA(cudaMemcpy(d + o_q, queries, qb, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d + o_r, refs, rb, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d + o_map, mapper, 256, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d + o_qo, query_off, (size_t)(n_queries + 1) * 4, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d + o_ro, ref_off, (size_t)(n_refs + 1) * 4, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d + o_mat, matrix, (size_t)msize * msize * 4, cudaMemcpyHostToDevice));
+    int32_t *d_out = (int32_t *)(d + o_out);
+    if (n_out == 3)
+        k_sg_batch<<<grid_for((long long)pairs, 128), 128>>>(d + o_q, (const int32_t *)(d + o_qo), n_queries, d + o_r,
+                                                            (const int32_t *)(d + o_ro), n_refs, open, extend,
+                                                            (const int32_t *)(d + o_mat), msize, d + o_map,
+                                                            d_out, d_out + pairs, d_out + 2 * pairs);
+    else
+        k_sg_stats_batch<<<grid_for((long long)pairs, 64), 64>>>(d + o_q, (const int32_t *)(d + o_qo), n_queries, d + o_r,
+                                                                (const int32_t *)(d + o_ro), n_refs, open, extend,
+                                                                (const int32_t *)(d + o_mat), msize, d + o_map, d_out);
     SG_CUDA(cudaGetLastError());
-    SG_CUDA(cudaMemcpy(score, d_out, pairs * 4, cudaMemcpyDeviceToHost));
-    SG_CUDA(cudaMemcpy(end_query, d_out + pairs, pairs * 4, cudaMemcpyDeviceToHost));
-    SG_CUDA(cudaMemcpy(end_ref, d_out + 2 * pairs, pairs * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n_out; ++i) SG_CUDA(cudaMemcpy(outs[i], d_out + (size_t)i * pairs, pairs * 4, cudaMemcpyDeviceToHost));
 #undef SG_CUDA
-    cleanup();
+    cudaFree(d);
     return 0;
+}
+
+int qcb_sg_batch(int device, const uint8_t *queries, const int32_t *query_off, int32_t n_queries,
+                 const uint8_t *refs, const int32_t *ref_off, int32_t n_refs, int32_t open, int32_t extend,
+                 const int32_t *matrix, int32_t msize, const uint8_t *mapper,
+                 int32_t *score, int32_t *end_query, int32_t *end_ref)
+{
+    int32_t *outs[3] = {score, end_query, end_ref};
+    return sg_batch_impl(device, queries, query_off, n_queries, refs, ref_off, n_refs, open, extend, matrix, msize, mapper, outs, 3);
+}
+
+int qcb_sg_stats_batch(int device, const uint8_t *queries, const int32_t *query_off, int32_t n_queries,
+                       const uint8_t *refs, const int32_t *ref_off, int32_t n_refs, int32_t open, int32_t extend,
+                       const int32_t *matrix, int32_t msize, const uint8_t *mapper,
+                       int32_t *score, int32_t *end_query, int32_t *end_ref, int32_t *matches, int32_t *similar, int32_t *length)
+{
+    int32_t *outs[6] = {score, end_query, end_ref, matches, similar, length};
+    return sg_batch_impl(device, queries, query_off, n_queries, refs, ref_off, n_refs, open, extend, matrix, msize, mapper, outs, 6);
 }
 
 int qcb_detect(qcb_plan *plan, const uint8_t *win5, const uint8_t *tail3, int32_t stride, const int32_t *wlen,

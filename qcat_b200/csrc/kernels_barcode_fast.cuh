@@ -211,22 +211,28 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr)
 // one LOP3 for the profile address (see kRowCodeMask), a pointer-compare loop, diagonal terms issued one column ahead
 // of the in-place max chain so that no register copies are needed.
 __global__ void __launch_bounds__(kBarcodeWarps * 32, 3)
-k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, int rows_min, int rows_cap,
-               const uint32_t *__restrict__ rowinfo, const int4 *__restrict__ taskmeta, int32_t *__restrict__ bc_score)
+k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, int rows_min, int rows_cap, int one_set,
+               int smem_profile_bytes, const uint32_t *__restrict__ rowinfo, const int4 *__restrict__ taskmeta,
+               int32_t *__restrict__ bc_score)
 {
     // rows_cap = DP rows (0..n) the shared-memory row tile of this launch holds; a tile is taken when its longest region
     // satisfies rows_min <= n < rows_cap, so a plan whose regions are almost always short (dual mode) can run them with a
     // small tile (three CTAs per SM) and leave the rare long ones to a second launch with the full tile.
+    // one_set = 0: the profiles of all core sets of the plan stay in shared memory (one or two sets: explicit kits, dual).
+    // one_set = 1 (many kits, `-k auto`): only the set of the tile at hand is resident -- after the kit vote a chunk's
+    // tiles nearly always share one set, so it is loaded once per CTA; a tile that mixes sets runs one pass per set.
     extern __shared__ __align__(1024) uint8_t smem_bc[];
     uint8_t *smem = smem_bc;
     uint32_t *s_prof = (uint32_t *)smem;                             // [pair][code][kProfRowBytes], 1 KB per pair
-    uint32_t *s_row = (uint32_t *)(smem + f.profile_bytes);          // [kRows][32] row-info words
+    uint32_t *s_row = (uint32_t *)(smem + smem_profile_bytes);       // [kRows][32] row-info words
     const uint32_t prof_addr = (uint32_t)__cvta_generic_to_shared(s_prof);
     const uint32_t row_addr = (uint32_t)__cvta_generic_to_shared(s_row);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < f.profile_bytes / 4; i += blockDim.x) s_prof[i] = f.profile[i];
+    if (!one_set)
+        for (int i = threadIdx.x; i < f.profile_bytes / 4; i += blockDim.x) s_prof[i] = f.profile[i];
+    int resident = -1;                         // one_set: byte offset of the core set whose profile is in shared memory
 
     const long long n_tasks = dual ? 2 * n_windows : n_windows;
     const long long n_tiles = (n_tasks + kRowTile - 1) / kRowTile;
@@ -238,12 +244,12 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
         int4 meta = make_int4(0, 0, 0, 0);
         if (task < n_tasks) meta = taskmeta[task];
         const FastGroup G = f.groups[meta.y < 0 ? 0 : meta.y];
-        int n = meta.y < 0 ? 0 : meta.x;
-        const int nmax = __reduce_max_sync(0xffffffffu, n);
-        if (__syncthreads_or(nmax >= rows_min && nmax < rows_cap) == 0) continue;   // nothing here for this launch
+        const int n_task = meta.y < 0 ? 0 : meta.x;
+        const int nmax_tile = __reduce_max_sync(0xffffffffu, n_task);
+        if (__syncthreads_or(nmax_tile >= rows_min && nmax_tile < rows_cap) == 0) continue;   // nothing here for this launch
         {
             const uint32_t *src = rowinfo + tile * (long long)(kRows * kRowTile);
-            const int words = (nmax + 1) * kRowTile;
+            const int words = (nmax_tile + 1) * kRowTile;
             for (int i = threadIdx.x; i < words; i += blockDim.x) s_row[i] = src[i];
         }
         __syncthreads();
@@ -251,52 +257,76 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
         decode_task((long long)(uint32_t)meta.w, n_windows, dual, w, k);      // the task behind this slot
         const int rup = meta.z;
         const int npairs = (G.nb + 1) >> 1;
-        const int npairs_max = __reduce_max_sync(0xffffffffu, n > 0 ? npairs : 0);
         const int v = G.u + (kCore - G.pad);            // last core column (template coordinates)
         int32_t *dst = bc_score + w * bslots + (k ? bmax0 : 0);
-        for (int pr = warp; pr < npairs_max; pr += (int)(blockDim.x >> 5)) {
-            const int pcl = min(pr, npairs - 1);
-            const uint32_t block = prof_addr + (uint32_t)G.prof_off + (uint32_t)pcl * kProfPairBytes;
-            uint32_t Wc[kCore];
+        unsigned todo = __ballot_sync(0xffffffffu, n_task > 0);               // the same in every warp of the CTA
+        while (todo) {
+            int n = n_task;
+            uint32_t set_base = (uint32_t)G.prof_off;
+            if (one_set) {
+                const int set = __reduce_min_sync(0xffffffffu, (todo >> lane) & 1u ? G.prof_off : INT32_MAX);
+                const bool mine = ((todo >> lane) & 1u) && G.prof_off == set;
+                const unsigned m_mine = __ballot_sync(0xffffffffu, mine);
+                if (set != resident) {                                         // uniform over the CTA
+                    const int set_pairs = __shfl_sync(0xffffffffu, npairs, __ffs(m_mine) - 1);
+                    __syncthreads();                                           // every warp is done with the old set
+                    const uint32_t *src = f.profile + set / 4;
+                    for (int i = threadIdx.x; i < set_pairs * (kProfPairBytes / 4); i += blockDim.x) s_prof[i] = src[i];
+                    resident = set;
+                    __syncthreads();
+                }
+                if (!mine) n = 0;
+                todo &= ~m_mine;
+                set_base = 0;
+            } else {
+                todo = 0;
+            }
+            const int nmax = __reduce_max_sync(0xffffffffu, n);
+            const int npairs_max = __reduce_max_sync(0xffffffffu, n > 0 ? npairs : 0);
+            for (int pr = warp; pr < npairs_max; pr += (int)(blockDim.x >> 5)) {
+                const int pcl = min(pr, npairs - 1);
+                const uint32_t block = prof_addr + set_base + (uint32_t)pcl * kProfPairBytes;
+                uint32_t Wc[kCore];
 #pragma unroll
-            for (int c = 0; c < kCore; ++c) Wc[c] = dup16((uint32_t)((G.u + max(0, c + 1 - G.pad)) * g));
-            const uint32_t info0 = s_row[lane];
-            uint32_t Fprev = dup16((info0 >> kRowFShift) & kRowFMask);
-            uint32_t acc = dup16((uint32_t)(v * g)) + dup16(info0 >> kRowGShift);  // join term of row 0
-            int i = 1;
-            while (i <= nmax) {
-                // rows up to the next row at which some lane's region ends run without per-lane branching; a lane's
-                // scores are taken at its own last row, so whatever it computes afterwards is never used
-                const int ev = __reduce_min_sync(0xffffffffu, n >= i ? n : INT32_MAX);
-                uint32_t rp = row_addr + (uint32_t)(i * kRowTile + lane) * 4u;
-                const uint32_t rp_end = row_addr + (uint32_t)((ev + 1) * kRowTile + lane) * 4u;
-                i = ev + 1;
+                for (int c = 0; c < kCore; ++c) Wc[c] = dup16((uint32_t)((G.u + max(0, c + 1 - G.pad)) * g));
+                const uint32_t info0 = s_row[lane];
+                uint32_t Fprev = dup16((info0 >> kRowFShift) & kRowFMask);
+                uint32_t acc = dup16((uint32_t)(v * g)) + dup16(info0 >> kRowGShift);  // join term of row 0
+                int i = 1;
+                while (i <= nmax) {
+                    // rows up to the next row at which some lane's region ends run without per-lane branching; a lane's
+                    // scores are taken at its own last row, so whatever it computes afterwards is never used
+                    const int ev = __reduce_min_sync(0xffffffffu, n >= i ? n : INT32_MAX);
+                    uint32_t rp = row_addr + (uint32_t)(i * kRowTile + lane) * 4u;
+                    const uint32_t rp_end = row_addr + (uint32_t)((ev + 1) * kRowTile + lane) * 4u;
+                    i = ev + 1;
 #pragma unroll 1
-                do {
-                    const uint32_t info = lds32(rp);
-                    rp += kRowTile * 4;
-                    const uint32_t prow = block | (info & kRowCodeMask);
-                    const uint32_t Fi = dup16((info >> kRowFShift) & kRowFMask);
-                    const uint32_t Gi = dup16(info >> kRowGShift);
-                    uint32_t e[kCore];
+                    do {
+                        const uint32_t info = lds32(rp);
+                        rp += kRowTile * 4;
+                        const uint32_t prow = block | (info & kRowCodeMask);
+                        const uint32_t Fi = dup16((info >> kRowFShift) & kRowFMask);
+                        const uint32_t Gi = dup16(info >> kRowGShift);
+                        uint32_t e[kCore];
 #pragma unroll
-                    for (int c = 0; c < kCore; c += 4) {
-                        const uint4 q = lds128(prow + c * 4);
-                        e[c] = q.x; e[c + 1] = q.y; e[c + 2] = q.z; e[c + 3] = q.w;
-                    }
-                    uint32_t left = Fi;
-                    uint32_t t = e[0] + Fprev;
+                        for (int c = 0; c < kCore; c += 4) {
+                            const uint4 q = lds128(prow + c * 4);
+                            e[c] = q.x; e[c + 1] = q.y; e[c + 2] = q.z; e[c + 3] = q.w;
+                        }
+                        uint32_t left = Fi;
+                        uint32_t t = e[0] + Fprev;
 #pragma unroll
-                    for (int c = 0; c < kCore; ++c) {
-                        const uint32_t tn = c + 1 < kCore ? e[c + 1] + Wc[c] : 0u;   // next column's diagonal term first
-                        left = __vimax3_u16x2(t, Wc[c], left);
-                        Wc[c] = left;
-                        t = tn;
-                    }
-                    Fprev = Fi;
-                    acc = __viaddmax_u16x2(left, Gi, acc);
-                } while (rp != rp_end);
-                if (n == ev && pr < npairs) store_pair_scores(Wc, acc, G, n, g, rup, pr, dst);
+                        for (int c = 0; c < kCore; ++c) {
+                            const uint32_t tn = c + 1 < kCore ? e[c + 1] + Wc[c] : 0u;   // next column's diagonal term first
+                            left = __vimax3_u16x2(t, Wc[c], left);
+                            Wc[c] = left;
+                            t = tn;
+                        }
+                        Fprev = Fi;
+                        acc = __viaddmax_u16x2(left, Gi, acc);
+                    } while (rp != rp_end);
+                    if (n == ev && pr < npairs) store_pair_scores(Wc, acc, G, n, g, rup, pr, dst);
+                }
             }
         }
     }

@@ -51,12 +51,17 @@ struct FastDev {
     int32_t n_groups;
 };
 
-struct AdapterSubset {       // packed adapter profile for one layout subset (pairs of consecutive subset entries)
+struct AdapterClass {        // the templates of one length class (NC register columns), two per lane
+    int nc_cols = 0, npairs = 0, row_words = 0;
+    size_t profile_bytes = 0;    // profile words; followed by npairs int4 {len lo, len hi, output slot lo, output slot hi (-1: none)}
+    size_t offset = 0;           // byte offset inside AdapterSubset::dev
+};
+
+struct AdapterSubset {       // packed adapter profiles for one layout subset, grouped by template length
     std::vector<int32_t> key;
-    void *dev = nullptr;      // profile words followed by int4 pair meta
+    void *dev = nullptr;
     size_t bytes = 0;
-    int npairs = 0, nc_cols = 0, row_words = 0;
-    size_t profile_bytes = 0;
+    std::vector<AdapterClass> classes;
     std::vector<uint8_t> host;   // staging copy (kept alive for the async upload)
 };
 
@@ -70,6 +75,8 @@ struct FastPlan {
     int sm_count = 0;
     size_t barcode_smem = 0;
     int max_pairs = 1;               // barcode pairs of the largest template group
+    bool one_set = false;            // k_barcode_fast keeps one core set's profile in shared memory at a time (many kits)
+    size_t profile_smem = 0;         // bytes of the profile region of k_barcode_fast's shared memory
     int short_rows = 0;              // > 0: row-tile size of the first of two k_barcode_fast launches (dual mode)
     int bucket_rows = kRows;         // regions shorter than this go to the front of the task order (k_task_order)
     const uint32_t *ctx_tab = nullptr;   // device: k_context score tables
@@ -134,7 +141,7 @@ k_adapter_fast(const uint32_t *__restrict__ profile, int profile_words, int row_
     for (long long task = (long long)blockIdx.x * kAdapterWarps + warp; task < n_tasks; task += warp_stride) {
         const long long tile = task / npairs;
         const int q = (int)(task % npairs);
-        const int4 meta = pair_meta[q];                 // x = len lo, y = len hi, z = has hi
+        const int4 meta = pair_meta[q];                 // x = len lo, y = len hi, z / w = output slots (w < 0: no second template)
         const int m_lo = meta.x, m_hi = meta.y;
         const long long w = tile * kTile + lane;
         const bool valid = w < n_windows;
@@ -199,7 +206,7 @@ k_adapter_fast(const uint32_t *__restrict__ profile, int profile_words, int row_
                     }
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        if (h == 1 && !meta.z) break;
+                        if (h == 1 && meta.w < 0) break;
                         const int m = h ? m_hi : m_lo;
                         const int best = h ? best_hi : best_lo, rb = h ? rb_hi : rb_lo;
                         const int C = (best >> 8) - m * g, iC = 255 - (best & 255);
@@ -207,7 +214,7 @@ k_adapter_fast(const uint32_t *__restrict__ profile, int profile_words, int row_
                         int score, end;
                         if (C > R) { score = C; end = iC - 1; }
                         else { score = R; end = n - 1; if (jR == m) end = iC - 1; }
-                        const long long o = w * n_subset + 2 * q + h;
+                        const long long o = w * n_subset + (h ? meta.w : meta.z);
                         ad_score[o] = score;
                         ad_end[o] = end;
                     }
@@ -292,6 +299,8 @@ inline void fast_adapter_prepare(FastPlan &fp, const qcb_tables *h)
 inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
 {
     fp.sm_count = sm_count;
+    fp.adapter_ok = fp.barcode_ok = false;
+    if (h->mode == QCB_MODE_SIMPLE) return 0;       // simple mode runs on the generic kernels (needs end_query per barcode)
     fast_adapter_prepare(fp, h);
     fp.barcode_ok = false;
     const int g = h->barcode_open;
@@ -428,7 +437,11 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
         fp.bucket_rows = std::min(rows, kRows);
         if (h->mode == QCB_MODE_DUAL && rows < kRows / 2) fp.short_rows = rows;
     }
-    fp.barcode_smem = profile_bytes + (size_t)kRows * kRowTile * 4;
+    // All core sets resident while they leave room for three CTAs per SM (explicit kits: one set; dual: two); plans with
+    // many sets (`-k auto`: every kit's) keep only the set of the tile at hand in shared memory.
+    fp.one_set = profile_bytes > 64 * 1024;
+    fp.profile_smem = fp.one_set ? (size_t)fp.max_pairs * kProfPairBytes : profile_bytes;
+    fp.barcode_smem = fp.profile_smem + (size_t)kRows * kRowTile * 4;
     if (fp.barcode_smem > 220 * 1024) return 0;
     // Opt every packed kernel into the device's full dynamic shared memory once.  The attribute is a per-device, per-
     // kernel maximum shared by all plans of the process, so it must never be lowered to one plan's own need.
@@ -449,6 +462,8 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     return 0;
 }
 
+inline int adapter_class_columns(int len) { return len <= 48 ? 48 : (len <= 64 ? 64 : 104); }
+
 inline AdapterSubset *adapter_subset(FastPlan &fp, const int32_t *h_subset, int n_subset, cudaStream_t st)
 {
     std::vector<int32_t> key(h_subset, h_subset + n_subset);
@@ -456,28 +471,38 @@ inline AdapterSubset *adapter_subset(FastPlan &fp, const int32_t *h_subset, int 
         if (sub->key == key) return sub;
     AdapterSubset *sub = new AdapterSubset();
     sub->key = key;
-    int mlen = 0;
-    for (int v : key) mlen = std::max(mlen, (int)fp.a_seq[v].size());
-    const int NC = mlen <= 48 ? 48 : (mlen <= 64 ? 64 : 104);
-    const int row_words = NC + 4, nc = fp.a_codes, g = fp.a_gap;
-    const int npairs = (n_subset + 1) / 2;
-    sub->npairs = npairs; sub->nc_cols = NC; sub->row_words = row_words;
-    sub->profile_bytes = (size_t)npairs * nc * row_words * 4;
-    sub->host.assign(sub->profile_bytes + (size_t)npairs * 16, 0);
-    uint32_t *prof = (uint32_t *)sub->host.data();
-    int32_t *meta = (int32_t *)(sub->host.data() + sub->profile_bytes);
-    for (int q = 0; q < npairs; ++q) {
-        const std::vector<uint8_t> &A = fp.a_seq[key[2 * q]];
-        const bool has_hi = 2 * q + 1 < n_subset;
-        const std::vector<uint8_t> &B = fp.a_seq[key[has_hi ? 2 * q + 1 : 2 * q]];
-        meta[q * 4 + 0] = (int)A.size(); meta[q * 4 + 1] = (int)B.size(); meta[q * 4 + 2] = has_hi ? 1 : 0;
-        for (int code = 0; code < nc; ++code)
-            for (int c = 0; c < NC; ++c) {
-                int ja = c - (NC - (int)A.size()), jb = c - (NC - (int)B.size());
-                uint32_t lo = ja >= 0 ? (uint32_t)(fp.a_mat[code * nc + fp.a_map[A[ja]]] + 2 * g) : 0u;
-                uint32_t hi = jb >= 0 ? (uint32_t)(fp.a_mat[code * nc + fp.a_map[B[jb]]] + 2 * g) : 0u;
-                prof[((size_t)q * nc + code) * row_words + c] = lo | (hi << 16);
-            }
+    const int nc = fp.a_codes, g = fp.a_gap;
+    // Templates are grouped by length class (48 / 64 / 104 register columns) and paired inside their class, shortest
+    // first, so that a 39-nt adapter does not pay for the 90-nt one next to it in the subset (`-k auto`: 12 layouts).
+    for (int NC : {48, 64, 104}) {
+        std::vector<int> slots;
+        for (int i = 0; i < n_subset; ++i)
+            if (adapter_class_columns((int)fp.a_seq[key[i]].size()) == NC) slots.push_back(i);
+        if (slots.empty()) continue;
+        std::stable_sort(slots.begin(), slots.end(), [&](int a, int b) { return fp.a_seq[key[a]].size() < fp.a_seq[key[b]].size(); });
+        AdapterClass cls;
+        cls.nc_cols = NC; cls.row_words = NC + 4; cls.npairs = ((int)slots.size() + 1) / 2;
+        cls.profile_bytes = (size_t)cls.npairs * nc * cls.row_words * 4;
+        cls.offset = (sub->host.size() + 255) / 256 * 256;
+        sub->host.resize(cls.offset + cls.profile_bytes + (size_t)cls.npairs * 16, 0);
+        uint32_t *prof = (uint32_t *)(sub->host.data() + cls.offset);
+        int32_t *meta = (int32_t *)(sub->host.data() + cls.offset + cls.profile_bytes);
+        for (int q = 0; q < cls.npairs; ++q) {
+            const int slot_lo = slots[2 * q];
+            const bool has_hi = 2 * q + 1 < (int)slots.size();
+            const int slot_hi = has_hi ? slots[2 * q + 1] : slot_lo;
+            const std::vector<uint8_t> &A = fp.a_seq[key[slot_lo]], &B = fp.a_seq[key[slot_hi]];
+            meta[q * 4 + 0] = (int)A.size(); meta[q * 4 + 1] = (int)B.size();
+            meta[q * 4 + 2] = slot_lo; meta[q * 4 + 3] = has_hi ? slot_hi : -1;
+            for (int code = 0; code < nc; ++code)
+                for (int c = 0; c < NC; ++c) {
+                    int ja = c - (NC - (int)A.size()), jb = c - (NC - (int)B.size());
+                    uint32_t lo = ja >= 0 ? (uint32_t)(fp.a_mat[code * nc + fp.a_map[A[ja]]] + 2 * g) : 0u;
+                    uint32_t hi = jb >= 0 ? (uint32_t)(fp.a_mat[code * nc + fp.a_map[B[jb]]] + 2 * g) : 0u;
+                    prof[((size_t)q * nc + code) * cls.row_words + c] = lo | (hi << 16);
+                }
+        }
+        sub->classes.push_back(cls);
     }
     sub->bytes = sub->host.size();
     if (cudaMalloc(&sub->dev, sub->bytes) != cudaSuccess) { delete sub; return nullptr; }
@@ -489,10 +514,11 @@ inline AdapterSubset *adapter_subset(FastPlan &fp, const int32_t *h_subset, int 
 }
 
 template <int NC>
-inline int launch_adapter_fast(FastPlan &fp, AdapterSubset *sub, const uint8_t *codes, int stride, const int32_t *wlen, int wshift,
-                               long long n_windows, int n_subset, int32_t *ad_score, int32_t *ad_end, cudaStream_t st)
+inline int launch_adapter_fast(FastPlan &fp, AdapterSubset *sub, const AdapterClass &cls, const uint8_t *codes, int stride,
+                               const int32_t *wlen, int wshift, long long n_windows, int n_subset, int32_t *ad_score,
+                               int32_t *ad_end, cudaStream_t st)
 {
-    const size_t smem = sub->profile_bytes + (size_t)kAdapterWarps * kRows * kTile;
+    const size_t smem = cls.profile_bytes + (size_t)kAdapterWarps * kRows * kTile;
     // opt into the device's full dynamic shared memory (a per-device, per-kernel maximum shared by all plans: never lower it)
     bool &configured = fp.adapter_smem_configured[NC <= 48 ? 0 : (NC <= 64 ? 1 : 2)];
     if (!configured) {
@@ -503,14 +529,15 @@ inline int launch_adapter_fast(FastPlan &fp, AdapterSubset *sub, const uint8_t *
         configured = true;
     }
     const long long n_tiles = (n_windows + kTile - 1) / kTile;
-    const long long n_tasks = n_tiles * sub->npairs;
+    const long long n_tasks = n_tiles * cls.npairs;
     int per_sm = NC <= 48 ? 6 : (NC <= 64 ? 5 : 3);
     while (per_sm > 1 && per_sm * smem > 200 * 1024) --per_sm;
     const int grid = (int)std::min<long long>((n_tasks + kAdapterWarps - 1) / kAdapterWarps, (long long)fp.sm_count * per_sm);
     if (grid <= 0) return 0;
-    k_adapter_fast<NC><<<grid, kAdapterWarps * 32, smem, st>>>((const uint32_t *)sub->dev, (int)(sub->profile_bytes / 4), sub->row_words,
-                                                             fp.a_codes, (const int4 *)((const uint8_t *)sub->dev + sub->profile_bytes),
-                                                             sub->npairs, codes, stride, wlen, wshift, n_windows, n_subset, fp.a_gap,
+    const uint8_t *base = (const uint8_t *)sub->dev + cls.offset;
+    k_adapter_fast<NC><<<grid, kAdapterWarps * 32, smem, st>>>((const uint32_t *)base, (int)(cls.profile_bytes / 4), cls.row_words,
+                                                             fp.a_codes, (const int4 *)(base + cls.profile_bytes),
+                                                             cls.npairs, codes, stride, wlen, wshift, n_windows, n_subset, fp.a_gap,
                                                              ad_score, ad_end);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -521,13 +548,17 @@ inline int fast_adapter_stage(FastPlan &fp, const DevTables &, const uint8_t *co
 {
     AdapterSubset *sub = adapter_subset(fp, h_subset, n_subset, st);
     if (!sub) return 1;
-    if (sub->profile_bytes + (size_t)kAdapterWarps * kRows * kTile > 200 * 1024) return 2;    // caller falls back
-    int rc;
-    if (sub->nc_cols == 48) rc = launch_adapter_fast<48>(fp, sub, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
-    else if (sub->nc_cols == 64) rc = launch_adapter_fast<64>(fp, sub, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
-    else rc = launch_adapter_fast<104>(fp, sub, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
-    if (rc == 0) ++*launches;
-    return rc;
+    for (const AdapterClass &cls : sub->classes)
+        if (cls.profile_bytes + (size_t)kAdapterWarps * kRows * kTile > 200 * 1024) return 2;    // caller falls back
+    for (const AdapterClass &cls : sub->classes) {
+        int rc;
+        if (cls.nc_cols == 48) rc = launch_adapter_fast<48>(fp, sub, cls, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
+        else if (cls.nc_cols == 64) rc = launch_adapter_fast<64>(fp, sub, cls, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
+        else rc = launch_adapter_fast<104>(fp, sub, cls, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
+        if (rc) return rc;
+        ++*launches;
+    }
+    return 0;
 }
 
 // Shared-context columns of every (window, set) task -> plan-owned rowinfo / taskmeta buffers.
@@ -598,7 +629,7 @@ inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, long long n_wind
             if (waste < best_waste) { best_waste = waste; warps = wc; }
         }
         const size_t regs_per_cta = (size_t)warps * 32 * 80;
-        const size_t profile_bytes = fp.barcode_smem - (size_t)kRows * kRowTile * 4;
+        const size_t profile_bytes = fp.profile_smem;
         const int passes = fp.short_rows > 0 ? 2 : 1;
         for (int pass = 0; pass < passes; ++pass) {
             const int rows_min = pass == 0 ? 1 : fp.short_rows;
@@ -607,7 +638,8 @@ inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, long long n_wind
             int ctas_per_sm = (int)std::min<size_t>((220 * 1024) / std::max<size_t>(1, smem), 65536 / regs_per_cta);
             ctas_per_sm = std::max(1, std::min(ctas_per_sm, 8));
             int grid = (int)std::min<long long>(n_tiles, (long long)fp.sm_count * ctas_per_sm);
-            k_barcode_fast<<<grid, warps * 32, smem, st>>>(fp.dev, n_windows, dual, bmax0, bslots, rows_min, rows_cap, rowinfo, taskmeta, bc_score);
+            k_barcode_fast<<<grid, warps * 32, smem, st>>>(fp.dev, n_windows, dual, bmax0, bslots, rows_min, rows_cap, fp.one_set ? 1 : 0,
+                                                           (int)profile_bytes, rowinfo, taskmeta, bc_score);
             ++*launches;
         }
     }

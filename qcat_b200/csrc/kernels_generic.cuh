@@ -78,6 +78,79 @@ __global__ void k_sg_batch(const uint8_t *__restrict__ queries, const int32_t *_
     score[id] = sc; end_query[id] = eq; end_ref[id] = er;
 }
 
+// parasail `sg_stats` (scanner_base.py:20-26; used by the simple scanner through find_highest_scoring_barcode
+// (compute_identity=True, :106-123) and by align_adapter_identity :144-188): sg_affine plus the number of exact matches,
+// of positive-scoring columns and the length of the alignment, carried along the predecessor the recurrence follows
+// (gap opened only when strictly better than extended; diagonal when >= both gap states, else F when F >= E, else E --
+// the oracle's qo_sg_stats states the same rule and its "parity unpinned" status).
+struct StatCell { int32_t h, m, s, l; };
+
+__device__ __forceinline__ void sg_affine_stats(const uint8_t *__restrict__ q, int n, const uint8_t *__restrict__ ref, int m,
+                                                int open, int extend, const int32_t *__restrict__ matrix, int msize,
+                                                const uint8_t *__restrict__ mapper,
+                                                int &score, int &end_query, int &end_ref, int &matches, int &similar, int &length)
+{
+    matches = 0; similar = 0; length = 0;
+    if (n <= 0 || m <= 0) { score = 0; end_query = -1; end_ref = -1; return; }
+    StatCell H[kMaxTemplate + 1];
+    StatCell F[kMaxTemplate + 1];
+    uint8_t rc[kMaxTemplate];
+    for (int j = 0; j < m; ++j) rc[j] = mapper[ref[j]];
+    for (int j = 0; j <= m; ++j) { H[j] = StatCell{0, 0, 0, 0}; F[j] = StatCell{kNegInf, 0, 0, 0}; }
+    StatCell col_best{INT32_MIN, 0, 0, 0};
+    int col_arg = -1;
+    for (int i = 1; i <= n; ++i) {
+        const int c1 = mapper[q[i - 1]];
+        const int32_t *row = matrix + msize * c1;
+        StatCell diag = H[0], left{0, 0, 0, 0}, E{kNegInf, 0, 0, 0};
+        for (int j = 1; j <= m; ++j) {
+            const StatCell up = H[j];
+            StatCell f, e, h;
+            if (up.h - open > F[j].h - extend) { f = up; f.h = up.h - open; } else { f = F[j]; f.h = F[j].h - extend; }
+            f.l += 1;
+            if (left.h - open > E.h - extend) { e = left; e.h = left.h - open; } else { e = E; e.h = E.h - extend; }
+            e.l += 1;
+            const int sub = row[rc[j - 1]];
+            const int d = diag.h + sub;
+            if (d >= e.h && d >= f.h) h = StatCell{d, diag.m + (c1 == rc[j - 1] ? 1 : 0), diag.s + (sub > 0 ? 1 : 0), diag.l + 1};
+            else if (f.h >= e.h) h = f;
+            else h = e;
+            F[j] = f; E = e; diag = up; H[j] = h; left = h;
+        }
+        if (left.h > col_best.h) { col_best = left; col_arg = i; }
+    }
+    int row_max = INT32_MIN, row_arg = -1;
+    for (int j = 1; j <= m; ++j)
+        if (H[j].h > row_max) { row_max = H[j].h; row_arg = j; }
+    StatCell end;
+    if (col_best.h > row_max) { score = col_best.h; end_query = col_arg - 1; end_ref = m - 1; end = col_best; }
+    else {
+        score = row_max; end_ref = row_arg - 1; end_query = n - 1; end = H[row_arg];
+        if (row_arg == m) { end_query = col_arg - 1; end = col_best; }
+    }
+    matches = end.m; similar = end.s; length = end.l;
+}
+
+// qcb_sg_stats_batch: every query against every reference, with the alignment statistics.
+__global__ void k_sg_stats_batch(const uint8_t *__restrict__ queries, const int32_t *__restrict__ qoff, int nq,
+                                 const uint8_t *__restrict__ refs, const int32_t *__restrict__ roff, int nr,
+                                 int open, int extend, const int32_t *__restrict__ matrix, int msize,
+                                 const uint8_t *__restrict__ mapper, int32_t *__restrict__ out /* [6][nq * nr] */)
+{
+    __shared__ int32_t s_mat[kMaxMatrix * kMaxMatrix];
+    __shared__ uint8_t s_map[256];
+    load_matrix_smem(s_mat, s_map, matrix, msize, mapper);
+    const long long pairs = (long long)nq * nr;
+    long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= pairs) return;
+    int qi = (int)(id / nr), ri = (int)(id % nr);
+    int sc, eq, er, mt, sm, ln;
+    sg_affine_stats(queries + qoff[qi], qoff[qi + 1] - qoff[qi], refs + roff[ri], roff[ri + 1] - roff[ri],
+                    open, extend, s_mat, msize, s_map, sc, eq, er, mt, sm, ln);
+    out[id] = sc; out[pairs + id] = eq; out[2 * pairs + id] = er; out[3 * pairs + id] = mt; out[4 * pairs + id] = sm;
+    out[5 * pairs + id] = ln;
+}
+
 // Window orientation: wins[2r] = read[:W], wins[2r+1] = revcomp(read[-W:]) (scanner_base.py:223-244, utils.py:26-27).
 __global__ void k_orient(const uint8_t *__restrict__ win5, const uint8_t *__restrict__ tail3, int stride,
                          const int32_t *__restrict__ wlen, long long n_reads, const uint8_t *__restrict__ comp,
@@ -274,11 +347,21 @@ __global__ void k_select(DevTables t, const int32_t *__restrict__ wlen, int wshi
     sel[w] = s;
 }
 
+// Simple mode (scanner_simple.py:47-92): no adapter stage; every barcode is aligned to the whole window.
+__global__ void k_select_simple(const int32_t *__restrict__ wlen, int wshift, long long n_windows, WindowSel *__restrict__ sel)
+{
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_windows) return;
+    WindowSel s;
+    s.layout = 0; s.end_query = -1; s.lo0 = 0; s.hi0 = max(wlen[w >> wshift], 0); s.lo1 = 0; s.hi1 = 0; s.full = 1; s.pad = 0;
+    sel[w] = s;
+}
+
 // Barcode stage, generic: one thread per (window, template slot); slots [0, B0) are set 0 and, in dual mode,
 // [bmax0, bmax0 + B1) are set 1 (find_highest_scoring_barcode's inner alignment, scanner_base.py:111-117).
 __global__ void k_barcode_generic(DevTables t, const uint8_t *__restrict__ wins, int stride, long long n_windows,
                                   const WindowSel *__restrict__ sel, int bmax0, int bslots,
-                                  int32_t *__restrict__ bc_score)
+                                  int32_t *__restrict__ bc_score, int32_t *__restrict__ bc_endq)
 {
     __shared__ int32_t s_mat[kMaxMatrix * kMaxMatrix];
     __shared__ uint8_t s_map[256];
@@ -300,6 +383,7 @@ __global__ void k_barcode_generic(DevTables t, const uint8_t *__restrict__ wins,
     sg_affine(wins + w * stride + lo, hi - lo, t.tmpl_seq + t.tmpl_off[tm], t.tmpl_off[tm + 1] - t.tmpl_off[tm],
               t.b_open, t.b_extend, s_mat, t.bmat_size, s_map, sc, eq, er);
     bc_score[id] = sc;
+    if (bc_endq) bc_endq[id] = eq;                       // simple mode keeps the winner's end_query (scanner_base.py:131)
 }
 
 struct EndResult {
@@ -333,13 +417,22 @@ __device__ __forceinline__ void pick_barcode(const DevTables &t, int g, int rlen
 }
 
 __device__ __forceinline__ EndResult scan_result(const DevTables &t, const WindowSel &s, int n,
-                                                 const int32_t *scores, int bmax0)
+                                                 const int32_t *scores, int bmax0, const int32_t *endq)
 {
     EndResult r;
     int L = s.layout;
     int g0 = t.group[L * 2];
     int b0; double s0;
     pick_barcode(t, g0, s.hi0 - s.lo0, scores, b0, s0);
+    if (t.mode == QCB_MODE_SIMPLE) {
+        // scanner_simple.py:67-92: what scan() calls `identity` is the third value returned at scanner_base.py:141 --
+        // the score -- so the threshold compares the score; the adapter is None, adapter_end is the barcode's end_query
+        if (s0 < t.min_quality) return empty_end();
+        r.layout = -1; r.barcode = b0; r.score = s0;
+        r.ident = b0 >= 0 ? t.tmpl_ident[t.group_off[g0] + b0] : -1;
+        r.adapter_end = b0 >= 0 ? endq[b0] : -1;
+        return r;
+    }
     if (t.mode == QCB_MODE_EPI2ME) {
         r.layout = L; r.barcode = b0; r.score = s0;
         r.ident = b0 >= 0 ? t.tmpl_ident[t.group_off[g0] + b0] : -1;
@@ -364,16 +457,17 @@ __device__ __forceinline__ EndResult scan_result(const DevTables &t, const Windo
 __global__ void k_finalize(DevTables t, const int32_t *__restrict__ wlen, const int64_t *__restrict__ read_len,
                            long long n_reads, const WindowSel *__restrict__ sel,
                            const int32_t *__restrict__ bc_score, int bmax0, int bslots,
-                           qcb_result *__restrict__ out)
+                           qcb_result *__restrict__ out, const int32_t *__restrict__ bc_endq)
 {
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     int n = wlen[r];
-    EndResult d5 = scan_result(t, sel[2 * r], n, bc_score + (2 * r) * bslots, bmax0);
+    EndResult d5 = scan_result(t, sel[2 * r], n, bc_score + (2 * r) * bslots, bmax0, bc_endq ? bc_endq + (2 * r) * bslots : nullptr);
     long long trim5 = 0;
     if (d5.adapter_end > 0) trim5 = d5.adapter_end;
     if (d5.score < t.min_quality) d5 = empty_end();
-    EndResult d3 = scan_result(t, sel[2 * r + 1], n, bc_score + (2 * r + 1) * bslots, bmax0);
+    EndResult d3 = scan_result(t, sel[2 * r + 1], n, bc_score + (2 * r + 1) * bslots, bmax0,
+                               bc_endq ? bc_endq + (2 * r + 1) * bslots : nullptr);
     long long trim3 = read_len[r];
     if (d3.layout >= 0 && d3.adapter_end > 0) trim3 -= d3.adapter_end;
     if (d3.score < t.min_quality) d3 = empty_end();
@@ -398,14 +492,14 @@ __global__ void k_finalize(DevTables t, const int32_t *__restrict__ wlen, const 
 // BarcodeScanner.scan for stand-alone windows: the per-window record before any two-end logic.
 __global__ void k_scan_out(DevTables t, const int32_t *__restrict__ wlen, long long n_windows,
                            const WindowSel *__restrict__ sel, const int32_t *__restrict__ bc_score, int bmax0, int bslots,
-                           qcb_result *__restrict__ out)
+                           qcb_result *__restrict__ out, const int32_t *__restrict__ bc_endq)
 {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_windows) return;
-    EndResult d = scan_result(t, sel[w], wlen[w], bc_score + w * bslots, bmax0);
+    EndResult d = scan_result(t, sel[w], wlen[w], bc_score + w * bslots, bmax0, bc_endq ? bc_endq + w * bslots : nullptr);
     qcb_result o;
     o.layout = d.layout; o.barcode = d.barcode; o.barcode_score = d.score; o.adapter_end = d.adapter_end;
-    o.trim5p = 0; o.trim3p = 0; o.exit_status = d.layout < 0 ? 1 : 0;
+    o.trim5p = 0; o.trim3p = 0; o.exit_status = (d.layout < 0 && d.barcode < 0) ? 1 : 0;
     out[w] = o;
 }
 
@@ -459,7 +553,7 @@ __global__ void k_histogram(const qcb_result *__restrict__ res, long long n_read
     if (r >= n_reads) return;
     qcb_result o = res[r];
     int bin = 0;
-    if (o.layout >= 0 && o.barcode >= 0) bin = 1 + layout_bin_base[o.layout] + o.barcode;
+    if (o.barcode >= 0) bin = 1 + (o.layout >= 0 ? layout_bin_base[o.layout] : 0) + o.barcode;   // layout -1: simple mode
     if (bin >= 0 && bin < n_bins) atomicAdd(counts + bin, 1ULL);
 }
 

@@ -1,6 +1,7 @@
 """Accelerate an installed nanoporetech/qcat in place.
 
-`install()` rebinds the detection entry points of qcat's own `BarcodeScannerEPI2ME` and `BarcodeScannerDual`
+`install()` rebinds the detection entry points of qcat's own `BarcodeScannerEPI2ME`, `BarcodeScannerDual` and
+`BarcodeScannerSimple`
 (detect_barcode, detect_barcode_batch, scan, scan_middle, detect_kit) to the GPU-backed implementations of
 `qcat_b200.scanner.GpuScannerMixin`.  Everything else -- the constructors (so `self.layouts` keeps the
 reference's own kit loading and ordering), `qcat.scanner.factory`, `qcat.cli` -- stays the reference's code,
@@ -19,7 +20,8 @@ def _targets():
     import qcat.scanner  # noqa: F401  (import order: scanner <-> scanner_epi2me cycle, see scanner.py:13)
     from qcat.scanner_dual import BarcodeScannerDual
     from qcat.scanner_epi2me import BarcodeScannerEPI2ME
-    return [BarcodeScannerEPI2ME, BarcodeScannerDual]
+    from qcat.scanner_simple import BarcodeScannerSimple
+    return [BarcodeScannerEPI2ME, BarcodeScannerDual, BarcodeScannerSimple]
 
 
 def install(device=None):

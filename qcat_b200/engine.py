@@ -27,9 +27,10 @@ def _vp(arr):
     return ctypes.c_void_p(arr.ctypes.data)
 
 
-def sg_batch(queries, refs, open, extend, matrix, device=None):
+def sg_batch(queries, refs, open, extend, matrix, device=None, stats=False):
     """Every query against every reference with parasail `sg` semantics -> (score, end_query, end_ref) int32
-    arrays of shape (len(queries), len(refs)).  `matrix` is a ScoreMatrix or parasail-like Matrix."""
+    arrays of shape (len(queries), len(refs)); stats=True (parasail `sg_stats`) adds (matches, similar, length).
+    `matrix` is a ScoreMatrix or parasail-like Matrix."""
     from qcat_b200.config import matrix_arrays
     lib = _ffi.load()
     msize, mat, mapper = matrix_arrays(matrix)
@@ -50,11 +51,14 @@ def sg_batch(queries, refs, open, extend, matrix, device=None):
     end_ref = np.zeros(shape, dtype=np.int32)
     mat = np.ascontiguousarray(mat, dtype=np.int32)
     mapper = np.ascontiguousarray(mapper, dtype=np.uint8)
-    _ffi.check(lib.qcb_sg_batch(default_device() if device is None else int(device),
-                                _vp(qbuf), _vp(qoff), len(queries), _vp(rbuf), _vp(roff), len(refs),
-                                int(open), int(extend), _vp(mat), msize, _vp(mapper),
-                                _vp(score), _vp(end_query), _vp(end_ref)))
-    return score, end_query, end_ref
+    args = (default_device() if device is None else int(device), _vp(qbuf), _vp(qoff), len(queries), _vp(rbuf), _vp(roff),
+            len(refs), int(open), int(extend), _vp(mat), msize, _vp(mapper), _vp(score), _vp(end_query), _vp(end_ref))
+    if not stats:
+        _ffi.check(lib.qcb_sg_batch(*args))
+        return score, end_query, end_ref
+    extra = [np.zeros(shape, dtype=np.int32) for _ in range(3)]
+    _ffi.check(lib.qcb_sg_stats_batch(*args, *[_vp(a) for a in extra]))
+    return (score, end_query, end_ref) + tuple(extra)
 
 
 class DevicePlan(object):
@@ -210,7 +214,7 @@ class DevicePlan(object):
         total = 0
         for i in range(t.n_layouts):
             base[i] = total
-            size = t.group_size(i, 0)
+            size = t.group_size(i, 0)               # simple mode: one placeholder layout, group 0 = the barcodes
             if t.mode == 1:
                 size *= t.group_size(i, 1)
             total += size

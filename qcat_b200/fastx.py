@@ -192,7 +192,8 @@ class _Labels(object):
                 name, bid = "barcode{:02d}/{:02d}".format(b[0].id, b[1].id), "{}/{}".format(b[0].id, b[1].id)
             else:
                 name, bid = b.name, str(b.id)
-            self.by_key[key] = (self.intern(name), self.intern(bid), self.intern(str(self.tables.layouts[layout_index].kit)))
+            kit = "none" if self.tables.mode == 2 else str(self.tables.layouts[layout_index].kit)   # simple: adapter None
+            self.by_key[key] = (self.intern(name), self.intern(bid), self.intern(kit))
         return self.by_key[key]
 
     def table(self):
@@ -254,7 +255,9 @@ def _score_chunk(scanner, plan, packed, batch_size, nobatch, chunk=None, qcat_co
     results = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
     names = [layout.kit for layout in scanner.layouts]
     kit_names = list(dict.fromkeys(names))
-    if nobatch or len(kit_names) == 1:
+    if tables.mode == 2:
+        plan.detect(win5, tail3, wlen, read_len, out=results)   # simple mode: no layouts, no vote (scanner_simple.py)
+    elif nobatch or len(kit_names) == 1:
         # no vote needed (single-read mode, or every layout names the same kit): one device call per chunk
         plan.detect(win5, tail3, wlen, read_len, scanner._subset_for(plan, scanner.layouts), out=results)
     elif tables.kit_index()[1] is not None and hasattr(plan, "detect_auto"):
@@ -286,8 +289,8 @@ def _filter_barcodes(tables, results, batch_size):
     """filter_barcodes per CLI batch (scanner_base.py:680-712): barcode ids seen in <= int(5 % of the most frequent
     key's count) reads -- "0" = unclassified counts as a key -- become empty results (trims reset to 0)."""
     n = len(results)
-    called = (results["layout"] >= 0) & (results["barcode"] >= 0)
-    key = results["layout"].astype(np.int64) * (1 << 32) + results["barcode"].astype(np.int64)
+    called = results["barcode"] >= 0                            # simple mode: a barcode without an adapter (layout -1)
+    key = np.maximum(results["layout"], 0).astype(np.int64) * (1 << 32) + results["barcode"].astype(np.int64)
     ids = np.zeros(n, dtype=np.int64)                           # 0 = unclassified (barcode ids start at 1)
     uniq, inverse = np.unique(key[called], return_inverse=True)
     id_of = {}
@@ -345,8 +348,8 @@ class _Writer(object):
     def emit(self, chunk, read_len, results):
         n = len(results)
         labels = self.labels
-        called = (results["layout"] >= 0) & (results["barcode"] >= 0)
-        key = results["layout"].astype(np.int64) * (1 << 32) + results["barcode"].astype(np.int64)
+        called = results["barcode"] >= 0                        # simple mode: a barcode without an adapter (layout -1)
+        key = np.maximum(results["layout"], 0).astype(np.int64) * (1 << 32) + results["barcode"].astype(np.int64)
         name_label = np.full(n, labels.none, dtype=np.int32)
         id_label = np.full(n, labels.none, dtype=np.int32)
         kit_label = np.full(n, labels.none, dtype=np.int32)
@@ -454,7 +457,8 @@ def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min
     failure = []
     # batches only matter when there is a kit vote or a per-batch barcode filter; chunks aligned to batches carry up to
     # one batch of bytes from chunk to chunk, so they are made larger
-    batched = not nobatch and (len(set(l.kit for l in scanner.layouts)) > 1 or getattr(scanner, "enable_filter_barcodes", False))
+    batched = not nobatch and ((plan.tables.mode != 2 and len(set(l.kit for l in scanner.layouts)) > 1) or
+                               getattr(scanner, "enable_filter_barcodes", False))
     multiple_of = batch_size if batched else 1
     if chunk_bytes is None:
         chunk_bytes = (256 << 20) if batched else (64 << 20)

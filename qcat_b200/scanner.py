@@ -10,6 +10,7 @@ classes have, so qcat_b200.dropin can graft it onto an installed qcat.
 """
 import logging
 import operator
+import os
 
 
 from qcat_b200 import adapters
@@ -59,21 +60,31 @@ class GpuScannerMixin(object):
     # ---- plan management ------------------------------------------------------------------------
 
     def _mode_name(self):
-        return "dual" if self.get_name() == "dual" else "epi2me"
+        name = self.get_name()
+        return name if name in ("dual", "simple") else "epi2me"
+
+    def _tables_for(self, qcat_config, layouts=None):
+        """(cache key, Tables factory) of this scanner for a config: simple mode flattens `self.barcodes` only
+        (scanner_simple.py never looks at a layout), the others their layouts (+ the epi2me barcode override)."""
+        mode = self._mode_name()
+        override = getattr(self, "barcodes", None)
+        if mode == "simple":
+            key = ("simple", tuple(override or ()), _config_key(qcat_config), float(self.min_quality), self.device)
+            return key, lambda: Tables.simple(override, qcat_config, self.min_quality)
+        layouts = self.layouts if layouts is None else layouts
+        key = (tuple(id(l) for l in layouts), _config_key(qcat_config), float(self.min_quality),
+               None if not override else tuple(override), mode, self.device)
+        return key, lambda: Tables(layouts, qcat_config, mode, self.min_quality, override)
 
     def _plan_for(self, qcat_config, layouts=None):
         from qcat_b200.engine import DevicePlan
-        layouts = self.layouts if layouts is None else layouts
-        override = getattr(self, "barcodes", None)
-        key = (tuple(id(l) for l in layouts), _config_key(qcat_config), float(self.min_quality),
-               None if not override else tuple(override), self._mode_name(), self.device)
+        key, make_tables = self._tables_for(qcat_config, layouts)
         cache = self.__dict__.setdefault("_qcb_plans", {})
         plan = cache.get(key)
         if plan is None:
             if len(cache) >= 4:
                 cache.pop(next(iter(cache))).close()
-            tables = Tables(layouts, qcat_config, self._mode_name(), self.min_quality, override)
-            plan = cache[key] = DevicePlan(tables, device=self.device)
+            plan = cache[key] = DevicePlan(make_tables(), device=self.device)
         return plan
 
     def _subset_for(self, plan, kits):
@@ -85,7 +96,10 @@ class GpuScannerMixin(object):
 
     def _record_to_dict(self, plan, rec):
         layout_index = int(rec["layout"])
-        if layout_index < 0:
+        if plan.tables.mode == 2:                 # simple: adapter None (scanner_simple.py:84-90)
+            result = build_return_dict(plan.tables.barcode_object(-1, int(rec["barcode"])), float(rec["barcode_score"]), None,
+                                       int(rec["adapter_end"]), int(rec["exit_status"]))
+        elif layout_index < 0:
             result = empty_return_dict()
             result["exit_status"] = int(rec["exit_status"])
         else:
@@ -106,6 +120,8 @@ class GpuScannerMixin(object):
         tables = plan.tables
         layouts = tables.layouts
         dual = tables.mode == 1
+        if tables.mode == 2:
+            return [self._record_to_dict(plan, rec) for rec in recs]
         barcodes = {}
         out = []
         for layout_index, barcode_index, score, adapter_end, trim5p, trim3p, exit_status in zip(
@@ -134,6 +150,9 @@ class GpuScannerMixin(object):
              qcat_config=None):
         """One window (any length) against the given layouts (scanner_epi2me.py:33 / scanner_dual.py:35)."""
         qcat_config = qcat_config or _default_config()
+        if self._mode_name() == "simple":             # scanner_simple.py:47-92 never looks at the templates
+            plan = self._plan_for(qcat_config)
+            return self._record_to_dict(plan, plan.scan_windows([read_sequence or ""], None)[0])
         if not isinstance(bc_adapter_templates, list):
             bc_adapter_templates = [bc_adapter_templates]
         if not bc_adapter_templates:
@@ -156,6 +175,8 @@ class GpuScannerMixin(object):
         return self.get_adapters(self.override_kit_name)
 
     def _detect_records(self, plan, packed, kits):
+        if plan.tables.mode == 2:
+            return plan.detect(*packed)
         if not kits:
             raise IndexError("list index out of range")          # scanner_epi2me.py:64 on an empty kit list
         win5, tail3, wlen, read_len = packed
@@ -279,8 +300,8 @@ class GpuScannerMixin(object):
         names = [layout.kit for layout in self.layouts]
         kit_names, kit_of_layout = plan.tables.kit_index()
         records = None
-        if not read_sequences:
-            kit_name = None
+        if not read_sequences or plan.tables.mode == 2:
+            kit_name = None                           # simple mode: the reference's vote never reaches scan()
         elif len(set(names)) == 1:
             kit_name = names[0]
         elif kit_of_layout is not None and hasattr(plan, "detect_auto"):
@@ -420,6 +441,31 @@ class BarcodeScannerDual(BarcodeScanner):
         return "dual"
 
 
+class BarcodeScannerSimple(BarcodeScanner):
+    """`--simple` (reference scanner_simple.py): bare barcodes against the window, no kit knowledge."""
+
+    def __init__(self, min_quality=None, kit_folder=None, kit=None, enable_filter_barcodes=False,
+                 scan_middle_adapter=False, threads=1, device=None):
+        if min_quality is None:
+            min_quality = 60
+        if threads != 1:
+            logging.warning("Multi threading is not yet supported in simple mode. Falling back to using a single thread.")
+        super(BarcodeScannerSimple, self).__init__(min_quality, None, kit_folder=kit_folder,
+                                                   enable_filter_barcodes=enable_filter_barcodes,
+                                                   scan_middle_adapter=scan_middle_adapter, device=device)
+        if os.path.isfile(kit) and os.path.exists(kit):             # kit=None raises TypeError like the reference
+            self.barcodes = adapters.get_barcodes_from_fastq(kit)
+        else:
+            self.barcodes = adapters.get_barcodes_simple(kit)
+
+    @staticmethod
+    def get_name():
+        return "simple"
+
+    def barcode_count(self):
+        return len(self.barcodes) + 1
+
+
 def get_adapter_by_name(kit, kit_folder=None):
     return [a for a in adapters.populate_adapter_layouts(kit_folder) if a.kit == kit]
 
@@ -446,7 +492,7 @@ def get_kits_info(kit_folder=None):
 def factory(mode="epi2me", min_quality=None, kit=None, kit_folder=None, enable_filter_barcodes=False,
             scan_middle_adapter=False, threads=1, device=None):
     """qcat.scanner.factory (reference scanner.py:78-111).  'guppy' falls back to epi2me as in the reference
-    when pyguppy is missing; the out-of-scope modes ('simple', 'brill') raise like any unknown mode."""
+    when pyguppy is missing; the out-of-scope mode 'brill' raises like any unknown mode."""
     if mode == "guppy":
         logging.warning("Demultiplexing mode {} currently not supported in your environment. "
                         "Falling back to epi2me.".format(mode))

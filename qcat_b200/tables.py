@@ -10,6 +10,7 @@ from qcat_b200.config import matrix_arrays
 
 MODE_EPI2ME = 0
 MODE_DUAL = 1
+MODE_SIMPLE = 2
 
 # utils.revcomp's translation table (reference utils.py:26-27): ACGT + IUPAC, both cases; anything else unchanged.
 _COMP_FROM = b"ACGTacgtRYMKrymkVBHDvbhd"
@@ -22,12 +23,53 @@ def _ascii(seq):
     return seq.encode("latin-1", "replace")
 
 
+class _SimpleLayout(object):
+    """Placeholder layout of simple mode (scanner_simple.py): no adapter, barcode set 0 = the scanner's `barcodes`,
+    aligned bare (no context) against the whole window."""
+    kit = "simple"
+    trim_offset = 0
+
+    def __init__(self, barcodes):
+        self._barcodes = list(barcodes)
+
+    def get_adapter_sequences(self):
+        return "N"
+
+    def get_adapter_length(self):
+        return 1
+
+    def get_barcode_length(self, k):
+        return 0
+
+    def get_barcode_end(self, k):
+        return -1
+
+    def is_double_barcode(self):
+        return False
+
+    def get_barcode_set(self, k):
+        return self._barcodes if k == 0 else None
+
+    def get_upstream_context(self, n, k):
+        return ""
+
+    def get_downstream_context(self, n, k):
+        return ""
+
+
 class Tables(object):
     """Numpy arrays (see qcb_tables) plus the Python objects the result records index into."""
 
+    @classmethod
+    def simple(cls, barcodes, qcat_config, min_quality):
+        """Tables of a simple-mode scanner (scanner_simple.py): one placeholder layout, group 0 = the bare barcodes."""
+        if not barcodes:
+            raise ValueError("simple mode needs at least one barcode")
+        return cls([_SimpleLayout(barcodes)], qcat_config, MODE_SIMPLE, min_quality)
+
     def __init__(self, layouts, qcat_config, mode, min_quality, barcodes_override=None):
         self.layouts = list(layouts)
-        self.mode = MODE_DUAL if mode in (MODE_DUAL, "dual") else MODE_EPI2ME
+        self.mode = MODE_DUAL if mode in (MODE_DUAL, "dual") else (MODE_SIMPLE if mode in (MODE_SIMPLE, "simple") else MODE_EPI2ME)
         self.min_quality = float(min_quality)
         cfg = qcat_config
         self.max_align_length = int(cfg.max_align_length)
@@ -122,6 +164,8 @@ class Tables(object):
 
     def barcode_object(self, layout_index, barcode_index):
         """Map a result record's (layout, barcode) back to the Barcode object(s) held by the layouts."""
+        if self.mode == MODE_SIMPLE:              # no adapter: records carry layout -1
+            return None if barcode_index < 0 else self.group_barcodes[0][barcode_index]
         if barcode_index < 0 or layout_index < 0:
             return None
         g1 = int(self.group[layout_index * 2])

@@ -23,7 +23,7 @@ def oracle_lib():
     global _oracle
     if _oracle is None:
         lib = ctypes.CDLL(oracle_build.build())
-        for name in ("qo_sg", "qo_detect", "qo_scan", "qo_kit_vote", "qo_find_best_adapter_template"):
+        for name in ("qo_sg", "qo_sg_stats", "qo_detect", "qo_scan", "qo_kit_vote", "qo_find_best_adapter_template"):
             getattr(lib, name).restype = None
         lib.qo_count_cells.restype = ctypes.c_int64
         _oracle = lib
@@ -124,6 +124,30 @@ def oracle_sg(query, ref, open, extend, matrix):
     lib.qo_sg(q, len(q), r, len(r), int(open), int(extend), _vp(mat), size, _vp(mapper),
               ctypes.byref(sc), ctypes.byref(eq), ctypes.byref(er))
     return sc.value, eq.value, er.value
+
+
+def oracle_sg_stats(query, ref, open, extend, matrix):
+    """qo_sg_stats -> (score, end_query, end_ref, matches, similar, length)."""
+    lib = oracle_lib()
+    size, mat, mapper = config.matrix_arrays(matrix)
+    q = query if isinstance(query, bytes) else query.encode("latin-1", "replace")
+    r = ref if isinstance(ref, bytes) else ref.encode("latin-1", "replace")
+    out = [ctypes.c_int32() for _ in range(6)]
+    mat = np.ascontiguousarray(mat, dtype=np.int32)
+    mapper = np.ascontiguousarray(mapper, dtype=np.uint8)
+    lib.qo_sg_stats(q, len(q), r, len(r), int(open), int(extend), _vp(mat), size, _vp(mapper), *[ctypes.byref(v) for v in out])
+    return tuple(v.value for v in out)
+
+
+def load_golden_simple():
+    data = np.load(os.path.join(ROOT, "tests", "golden", "golden_simple_v1.npz"))
+    return data, json.loads(bytes(data["cases"]).decode())["cases"]
+
+
+def simple_tables_for_case(case):
+    sc = scanner.BarcodeScannerSimple(min_quality=case["min_quality"], kit=case["kit"])
+    assert len(sc.barcodes) == case["n_barcodes"]
+    return Tables.simple(sc.barcodes, config.qcatConfig(), sc.min_quality), sc
 
 
 def load_golden():

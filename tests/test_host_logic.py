@@ -82,10 +82,13 @@ def test_kit_selection_and_factory():
     assert scanner.BarcodeScannerEPI2ME(kit="nonexistent").layouts == []
     assert scanner.factory(mode="dual").min_quality == 60 and scanner.factory().min_quality == 58
     assert scanner.factory(mode="guppy").get_name() == "epi2me"
-    assert sorted(scanner.get_modes()) == ["dual", "epi2me"]
+    assert sorted(scanner.get_modes()) == ["dual", "epi2me", "simple"]
     assert "PBC096" in scanner.get_kits() and scanner.get_kits()[0] == "Auto"
+    simple = scanner.factory(mode="simple", kit="standard")
+    assert simple.get_name() == "simple" and simple.min_quality == 60 and len(simple.barcodes) == 24
+    assert len(scanner.factory(mode="simple", kit="extended").barcodes) == 120
     with pytest.raises(RuntimeError):
-        scanner.factory(mode="simple")
+        scanner.factory(mode="brill")
 
 
 def test_pack_windows_is_extract_align_sequence():
