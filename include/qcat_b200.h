@@ -184,6 +184,26 @@ int qcb_detect_auto_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t 
                            const int32_t *kit_of_layout /* host */, int32_t batch_size, qcb_result *d_out,
                            int32_t *d_batch_kit, void *stream);
 
+/* The same calls spread over several devices inside one process: plans[d] was created on device d with the same tables;
+ * reads are dealt to the plans in blocks (>= 64 Ki reads, whole batches in the auto-kit call), round-robin, every plan
+ * runs its blocks through its own copy / compute pipeline on its own host thread, and every record is written at its
+ * read's own position in `out` (results in input order, scanner_base.py:714-733).  Reads are independent, so there is no
+ * device-to-device traffic on this path. */
+int qcb_detect_multi(qcb_plan *const *plans, int32_t n_plans, const uint8_t *win5, const uint8_t *tail3, int32_t stride,
+                     const int32_t *wlen, const int64_t *read_len, int64_t n_reads,
+                     const int32_t *subset, int32_t n_subset, qcb_result *out);
+
+int qcb_detect_auto_multi(qcb_plan *const *plans, int32_t n_plans, const uint8_t *win5, const uint8_t *tail3, int32_t stride,
+                          const int32_t *wlen, const int64_t *read_len, int64_t n_reads,
+                          const int32_t *kit_of_layout, int32_t batch_size, qcb_result *out, int32_t *batch_kit);
+
+/* The path's only exchange (the counts behind the CLI histogram, cli.py:386-405) for plans of one process: d_counts[d] =
+ * device d's int64[n_bins] vector (qcb_histogram_device), d_gathered[d] = device d's int64[n_plans * n_bins] buffer that
+ * receives every device's vector, written with peer copies (over NVLink where the devices are peers).  Synchronises.
+ * Between processes (one rank per GPU) the same all-gather is one NCCL call: qcat_b200.dist.allgather_counts. */
+int qcb_hist_allgather(qcb_plan *const *plans, int32_t n_plans, int64_t *const *d_counts, int32_t n_bins,
+                       int64_t *const *d_gathered);
+
 /* counts[bin] += 1 per record, bin = 0 for "none", 1 + layout_bin_base[layout] + barcode otherwise
  * (layout_bin_base: host array [n_layouts]).  d_counts must hold n_bins int64 and is NOT cleared. */
 int qcb_histogram_device(qcb_plan *plan, const qcb_result *d_results, int64_t n_reads,

@@ -2,8 +2,11 @@
 // entry points.  See include/qcat_b200.h for the contract and the reference interfaces each call replaces.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "plan.h"
@@ -284,10 +287,12 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
         StageTimer timer(p, 0, st);
         if (fast_ok) {
             if (p->codes.reserve((size_t)nw * stride)) return 1;
-            k_orient_codes<<<grid_for(nw * (stride / 4), 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, t.amap, t.bmap,
-                                                                          packed_only ? nullptr : (uint8_t *)p->wins.ptr, (uint8_t *)p->codes.ptr);
-        } else {
+            k_map_codes<<<grid_for(nw * (stride / 16), 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, t.amap, t.bmap,
+                                                                        (uint8_t *)p->codes.ptr);
+        }
+        if (!packed_only) {                  // a generic stage will run: it reads the oriented ASCII windows
             k_orient<<<grid_for(nw * stride, 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, (uint8_t *)p->wins.ptr);
+            if (fast_ok) p->launches++;
         }
         p->launches++;
         wins = (const uint8_t *)p->wins.ptr;
@@ -350,7 +355,7 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
     }
     if (fast_ok && p->fast.barcode_ok) {
         StageTimer timer(p, 5, st);
-        if (fast_context_stage(p->fast, t, (const uint8_t *)p->codes.ptr, stride, nw, sel, st, &p->launches))
+        if (fast_context_stage(p->fast, t, (const uint8_t *)p->codes.ptr, stride, d_wlen, nw, sel, st, &p->launches))
             return fail("shared-context stage launch failed");
     }
     {
@@ -463,43 +468,58 @@ int detect_device_impl(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail
     return 0;
 }
 
-// Host-buffer path: stage -> device pipeline -> copy back, chunk by chunk.
+// One device's share of a multi-device call: blocks of `block` reads starting at first, first + period, ...
+struct Shard { long long first, block, period; };
+
+int validate_wlen(const qcb_plan *p, const int32_t *wlen, int64_t n_reads, int32_t stride, bool window_mode)
+{
+    for (int64_t i = 0; i < n_reads; ++i) {
+        const int32_t len = wlen[i];
+        if (len < 0 || len > stride || (!window_mode && len > p->t.W))
+            return fail("wlen[%lld] = %d outside [0, %d]", (long long)i, len, window_mode ? stride : std::min<int>(stride, p->t.W));
+    }
+    return 0;
+}
+
 // Host-buffer path: H2D -> device pipeline -> D2H, chunk by chunk, software pipelined over three streams with
 // double-buffered staging so the copies of chunk k+1 / k-1 overlap the kernels of chunk k (pinned host memory makes
 // the copies truly asynchronous; pageable memory still works, just without the overlap).
 int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int32_t stride, const int32_t *wlen,
                      const int64_t *read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset,
                      qcb_result *out, int32_t *vote, const int32_t *kit_of_layout = nullptr, int32_t batch_size = 0,
-                     int32_t *batch_kit_out = nullptr)
+                     int32_t *batch_kit_out = nullptr, const Shard *shard = nullptr)
 {
     if (!p) return fail("plan is NULL");
     if (n_reads < 0) return fail("n_reads is negative");
     if (n_reads == 0) return 0;
     const bool window_mode = tail3 == nullptr;
     if (!win5 || !wlen || (!vote && !out) || (!vote && !window_mode && !read_len)) return fail("NULL input/output buffer");
-    for (int64_t i = 0; i < n_reads; ++i) {
-        const int32_t len = wlen[i];
-        if (len < 0 || len > stride || (!window_mode && len > p->t.W))
-            return fail("wlen[%lld] = %d outside [0, %d]", (long long)i, len, window_mode ? stride : std::min<int>(stride, p->t.W));
-    }
+    if (!shard && validate_wlen(p, wlen, n_reads, stride, window_mode)) return 1;
     QCB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = p->stream, s_in = p->copy_in, s_out = p->copy_out;
     // Pipeline granularity: at least 64 Ki reads per chunk (small kernels lose time in their last wave of tiles), larger
     // for big calls as long as ~8 chunks remain to overlap the copies with the kernels, never above the device chunk.
-    long long chunk = std::max<long long>(p->host_chunk_reads, (n_reads / 8 + 31) / 32 * 32);
+    static const long long chunk_div = getenv("QCB_HOST_CHUNK_DIV") ? std::max(1, atoi(getenv("QCB_HOST_CHUNK_DIV"))) : 8;
+    long long chunk = std::max<long long>(p->host_chunk_reads, (n_reads / chunk_div + 31) / 32 * 32);
     chunk = std::min<long long>(chunk, p->chunk_reads);
     if ((long long)stride * chunk > (1LL << 27)) chunk = std::max<long long>(1, (1LL << 27) / stride);
     const bool auto_mode = kit_of_layout != nullptr;
     const long long n_batches = auto_mode ? (n_reads + batch_size - 1) / batch_size : 0;
+    const long long span = shard ? shard->block : n_reads;       // reads this plan handles in one piece
     if (auto_mode) {
         // pipeline chunks are whole batches; a batch larger than a chunk goes to the device in one piece
         if (batch_size <= 0) return fail("batch_size must be positive");
-        chunk = batch_size <= chunk ? chunk / batch_size * batch_size : n_reads;
+        chunk = batch_size <= chunk ? chunk / batch_size * batch_size : span;
         if (p->auto_kit.reserve((size_t)n_batches * 4)) return 1;
+    }
+    // the chunks of this call: the whole input, or this device's blocks of a multi-device call
+    std::vector<std::pair<long long, long long>> chunks;
+    for (long long base = shard ? shard->first : 0; base < n_reads; base += shard ? shard->period : n_reads) {
+        const long long end = std::min<long long>(n_reads, base + span);
+        for (long long off = base; off < end; off += chunk) chunks.emplace_back(off, std::min<long long>(chunk, end - off));
     }
     const size_t out_item = vote ? 4 : sizeof(qcb_result);
     int rc = 0;
-    long long k = 0;
     // errors inside the loop must still reach the stream synchronisations below: async copies on the caller's
     // (pinned) buffers may be in flight
 #define LOOP_CUDA(call)                                                                                   \
@@ -507,9 +527,9 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
         cudaError_t e_ = (call);                                                                          \
         if (e_ != cudaSuccess) { rc = fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); break; } \
     }
-    for (long long off = 0; off < n_reads && !rc; off += chunk, ++k) {
+    for (size_t k = 0; k < chunks.size() && !rc; ++k) {
         const int b = (int)(k & 1);
-        long long n = std::min<long long>(chunk, n_reads - off);
+        const long long off = chunks[k].first, n = chunks[k].second;
         size_t b_win = (size_t)n * stride, b_len = (size_t)n * 4, b_rl = (size_t)n * 8;
         size_t o_tail = (b_win + 255) / 256 * 256, o_len = o_tail + (b_win + 255) / 256 * 256;
         size_t o_rl = o_len + (b_len + 255) / 256 * 256, total = o_rl + b_rl;
@@ -539,12 +559,13 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
         LOOP_CUDA(cudaStreamWaitEvent(s_out, p->ev_compute[b], 0));
         if (vote) { LOOP_CUDA(cudaMemcpyAsync(vote + off, d_res, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out)); }
         else { LOOP_CUDA(cudaMemcpyAsync(out + off, d_res, (size_t)n * sizeof(qcb_result), cudaMemcpyDeviceToHost, s_out)); }
+        if (auto_mode && batch_kit_out) {
+            const long long b0 = off / batch_size, nb = (n + batch_size - 1) / batch_size;
+            LOOP_CUDA(cudaMemcpyAsync(batch_kit_out + b0, (const int32_t *)p->auto_kit.ptr + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, s_out));
+        }
         LOOP_CUDA(cudaEventRecord(p->ev_d2h[b], s_out));
     }
 #undef LOOP_CUDA
-    if (!rc && auto_mode && batch_kit_out &&
-        cudaMemcpyAsync(batch_kit_out, p->auto_kit.ptr, (size_t)n_batches * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
-        rc = fail("copy of the per-batch kits failed");
     cudaError_t e1 = cudaStreamSynchronize(s_in), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(s_out);
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
@@ -767,6 +788,83 @@ int qcb_detect_auto_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t 
     AutoCall ac{kit_of_layout, batch_size, d_batch_kit};
     return detect_device_impl(plan, d_win5, d_tail3, stride, d_wlen, d_read_len, n_reads, nullptr, 0, d_out, nullptr,
                               (cudaStream_t)stream, &ac);
+}
+
+// One host thread per plan; plan d takes the blocks d, d + D, d + 2 D, ... of `block` reads (round-robin at block
+// granularity) through its own three-stream pipeline and writes its records at the reads' own positions.
+static int detect_multi_impl(qcb_plan *const *plans, int32_t n_plans, const uint8_t *win5, const uint8_t *tail3, int32_t stride,
+                             const int32_t *wlen, const int64_t *read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset,
+                             qcb_result *out, const int32_t *kit_of_layout, int32_t batch_size, int32_t *batch_kit)
+{
+    if (!plans || n_plans <= 0) return fail("no plans");
+    for (int d = 0; d < n_plans; ++d) if (!plans[d]) return fail("plan %d is NULL", d);
+    if (n_reads < 0) return fail("n_reads is negative");
+    if (n_reads == 0) return 0;
+    if (!win5 || !tail3 || !wlen || !read_len || !out) return fail("NULL input/output buffer");
+    if (kit_of_layout && batch_size <= 0) return fail("batch_size must be positive");
+    if (validate_wlen(plans[0], wlen, n_reads, stride, false)) return 1;
+    // block size: ~4 blocks per device for load balance, at least 64 Ki reads, whole CLI batches in auto-kit calls
+    long long block = std::max<long long>(1 << 16, (n_reads / (4LL * n_plans) + 31) / 32 * 32);
+    if (kit_of_layout) block = std::max<long long>(1, (block + batch_size - 1) / batch_size) * batch_size;
+    std::vector<int> rcs(n_plans, 0);
+    std::vector<std::string> errors(n_plans);
+    std::vector<std::thread> pool;
+    for (int d = 0; d < n_plans; ++d) {
+        pool.emplace_back([&, d]() {
+            const Shard shard{(long long)d * block, block, (long long)n_plans * block};
+            rcs[d] = detect_host_impl(plans[d], win5, tail3, stride, wlen, read_len, n_reads, subset, n_subset, out, nullptr,
+                                      kit_of_layout, batch_size, batch_kit, &shard);
+            if (rcs[d]) errors[d] = g_error;                   // thread-local message of the worker
+        });
+    }
+    for (auto &th : pool) th.join();
+    for (int d = 0; d < n_plans; ++d)
+        if (rcs[d]) return fail("device shard %d: %s", d, errors[d].c_str());
+    return 0;
+}
+
+int qcb_detect_multi(qcb_plan *const *plans, int32_t n_plans, const uint8_t *win5, const uint8_t *tail3, int32_t stride,
+                     const int32_t *wlen, const int64_t *read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset,
+                     qcb_result *out)
+{
+    return detect_multi_impl(plans, n_plans, win5, tail3, stride, wlen, read_len, n_reads, subset, n_subset, out, nullptr, 0, nullptr);
+}
+
+int qcb_detect_auto_multi(qcb_plan *const *plans, int32_t n_plans, const uint8_t *win5, const uint8_t *tail3, int32_t stride,
+                          const int32_t *wlen, const int64_t *read_len, int64_t n_reads, const int32_t *kit_of_layout,
+                          int32_t batch_size, qcb_result *out, int32_t *batch_kit)
+{
+    if (!kit_of_layout) return fail("kit_of_layout is NULL");
+    return detect_multi_impl(plans, n_plans, win5, tail3, stride, wlen, read_len, n_reads, nullptr, 0, out, kit_of_layout,
+                             batch_size, batch_kit);
+}
+
+// In-process all-gather of the per-device count vectors over peer copies (NVLink when the devices are peers).
+int qcb_hist_allgather(qcb_plan *const *plans, int32_t n_plans, int64_t *const *d_counts, int32_t n_bins, int64_t *const *d_gathered)
+{
+    if (!plans || n_plans <= 0 || !d_counts || !d_gathered || n_bins <= 0) return fail("bad argument");
+    for (int i = 0; i < n_plans; ++i) if (!plans[i] || !d_counts[i] || !d_gathered[i]) return fail("NULL entry %d", i);
+    const size_t bytes = (size_t)n_bins * sizeof(int64_t);
+    for (int i = 0; i < n_plans; ++i) {
+        QCB_CUDA(cudaSetDevice(plans[i]->device));
+        for (int j = 0; j < n_plans; ++j) {
+            if (plans[i]->device != plans[j]->device) {
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, plans[i]->device, plans[j]->device) == cudaSuccess && can) {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(plans[j]->device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                    else if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                }
+            }
+            QCB_CUDA(cudaMemcpyPeerAsync(d_gathered[i] + (size_t)j * n_bins, plans[i]->device, d_counts[j], plans[j]->device, bytes,
+                                         plans[i]->stream));
+        }
+    }
+    for (int i = 0; i < n_plans; ++i) {
+        QCB_CUDA(cudaSetDevice(plans[i]->device));
+        QCB_CUDA(cudaStreamSynchronize(plans[i]->stream));
+    }
+    return 0;
 }
 
 int qcb_scan(qcb_plan *plan, const uint8_t *windows, int32_t stride, const int32_t *wlen, int64_t n_windows,

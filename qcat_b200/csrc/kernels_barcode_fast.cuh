@@ -59,33 +59,67 @@ __global__ void k_task_order(DevTables t, const WindowSel *__restrict__ sel, lon
     perm[slot] = (uint32_t)task;
 }
 
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // Shared-context columns.  F[i] = H[i][u] + (i+u) g for the forward DP of region rows vs the shared prefix;
 // G[i] = H'[n-i][d] + (n-i+d) g for the DP of the reversed region vs the reversed shared suffix, whose left border
 // is 0 except -g at its last row (node (0, m) is not a valid end).  See DESIGN.md section 4.
 //
 // Packed: lane = one task, low u16 half = the F problem, high half = the G problem, both right-aligned in NCOL
-// registers (dead columns in front keep the border value).  Step s feeds region row s to F and row n-s+1 to G; the
-// per-group tables ctx_tab[grp][F|G][code][NCOL] hold the shifted scores (G's already moved to the high half), so a
-// cell is one three-input add and one VIMNMX3.U16x2.
+// registers (dead columns in front keep the border value).  Step s feeds region row s to F and row n-s+1 to G.
+// PAIR = true: one table word per column holds both shifted scores, ctx_tab[grp][code F][code G][NCOL], so a step costs
+// NCOL / 4 LDS.128 and a cell is one add and one VIMNMX3.U16x2; PAIR = false (too many groups for that table):
+// ctx_tab[grp][F | G][code][NCOL], two lookups and a three-input add per cell.
+// Output: row r of the packed row info needs F[r] (step r) and G[r] (step n - r).  The value that comes first waits in
+// shared memory, indexed by its step; the step that brings the second one assembles the word and stores it -- every row
+// is written once, nothing is read back from global memory.
 constexpr int kCtxWarps = 4;
+constexpr int kCtxEarlyRows = kRows / 2 + 1;                  // steps s with 2 s < n, plus slot 0 (the constant border values)
 
-template <int NCOL>
+template <int NCOL, bool PAIR>
 __global__ void __launch_bounds__(kCtxWarps * 32)
 k_context(FastDev f, DevTables t, const uint32_t *__restrict__ ctx_tab, const uint8_t *__restrict__ codes, int stride,
-          long long n_windows, const WindowSel *__restrict__ sel, int dual, const uint32_t *__restrict__ perm,
+          const int32_t *__restrict__ wlen, long long n_windows, const WindowSel *__restrict__ sel, int dual, const uint32_t *__restrict__ perm,
           uint32_t *__restrict__ rowinfo, int4 *__restrict__ taskmeta)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nc = f.n_codes, g = f.gap;
-    const int tab_words = f.n_groups * 2 * nc * NCOL;
+    const int grp_words = (PAIR ? nc * nc : 2 * nc) * NCOL;
+    const int tab_words = f.n_groups * grp_words;
     uint32_t *s_tab = (uint32_t *)smem;
-    uint8_t *s_code = smem + (size_t)tab_words * 4 + (size_t)warp * (kRows * kRowTile);
+    uint32_t *s_early = s_tab + tab_words + warp * (kCtxEarlyRows * kRowTile);
+    uint8_t *s_code = (uint8_t *)(s_tab + tab_words + kCtxWarps * (kCtxEarlyRows * kRowTile)) + (size_t)warp * (kRows * kRowTile);
     for (int i = threadIdx.x; i < tab_words; i += blockDim.x) s_tab[i] = ctx_tab[i];
     __syncthreads();
 
     const long long n_tasks = dual ? 2 * n_windows : n_windows;
     const long long n_tiles = (n_tasks + kRowTile - 1) / kRowTile;
+    constexpr uint32_t kLowMask = (1u << kRowGShift) - 1u;     // code | F of a row-info word
     for (long long tile = (long long)blockIdx.x * kCtxWarps + warp; tile < n_tiles; tile += (long long)gridDim.x * kCtxWarps) {
         const long long slot = tile * kRowTile + lane;          // position in the bucketed task order (k_task_order)
         const bool valid = slot < n_tasks;
@@ -100,53 +134,75 @@ k_context(FastDev f, DevTables t, const uint32_t *__restrict__ ctx_tab, const ui
         const FastGroup G = f.groups[grp < 0 ? 0 : grp];
         const int u = G.u, d = G.d;
         __syncwarp();
-        {   // the lane's whole window: barcode-matrix code = high nibble of the packed code byte
+        {   // the lane's window: barcode-matrix code = high nibble of the packed code byte.  3' windows (odd w) are stored
+            // unreversed by k_map_codes: base p of the stored window is position wl - 1 - p of the oriented one
             const uint4 *src = (const uint4 *)(codes + w * stride);
-            const int last = n > 0 ? lo + n : 0;
-            for (int ch = 0; ch * 16 < last; ++ch) {
+            const int wl = wlen[w >> 1];
+            const bool rev = (w & 1) != 0;
+            const int first = n > 0 ? (rev ? wl - (lo + n) : 0) : 0, last = n > 0 ? (rev ? wl - lo : lo + n) : 0;
+            for (int ch = max(first, 0) >> 4; ch * 16 < last; ++ch) {
                 const uint4 v = src[ch];
                 const uint32_t words[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int b = 0; b < 16; ++b)
-                    s_code[(ch * 16 + b + 1) * kRowTile + lane] = (uint8_t)((words[b >> 2] >> ((b & 3) * 8 + 4)) & 15u);
+                for (int b = 0; b < 16; ++b) {
+                    const int p = ch * 16 + b;
+                    const int pos = rev ? wl - 1 - p : p;                // position in the oriented window
+                    if (pos >= 0 && pos < kRows - 1) s_code[(pos + 1) * kRowTile + lane] = (uint8_t)((words[b >> 2] >> ((b & 3) * 8 + 4)) & 15u);
+                }
             }
         }
+        // slot 0 of the early values: F[0] (row 0, no base code) and G[n] (row 0 of the reversed problem)
+        s_early[lane] = ((uint32_t)(u * g) << kRowFShift) | ((uint32_t)(d * g) << kRowGShift);
+        if (n <= 0) s_code[kRowTile + lane] = 0;                     // idle lanes read row 1 in the step loop
         __syncwarp();
         const int nmax = __reduce_max_sync(0xffffffffu, n);
-        const uint32_t *tabF = s_tab + (size_t)(grp < 0 ? 0 : grp) * 2 * nc * NCOL;
-        const uint32_t *tabG = tabF + nc * NCOL;
+        // shared-memory byte addresses (explicit shared-space loads: no generic-address arithmetic in the step loop)
+        const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(s_tab) + (uint32_t)(grp < 0 ? 0 : grp) * grp_words * 4u;
+        const uint32_t early_addr = (uint32_t)__cvta_generic_to_shared(s_early) + lane * 4u;
+        const uint32_t code_addr = (uint32_t)__cvta_generic_to_shared(s_code) + lane;
         uint32_t Wc[NCOL];
 #pragma unroll
         for (int c = 0; c < NCOL; ++c) {
             const int jf = c - (NCOL - u) + 1, jg = c - (NCOL - d) + 1;
             Wc[c] = (uint32_t)(max(jf, 0) * g) | ((uint32_t)(max(jg, 0) * g) << 16);
         }
-        // Row r of the packed output receives F at step r and G at step n - r.  Whichever comes first is a plain store,
-        // the later one ORs into it (same thread, so program order makes the read see the earlier store).
         uint32_t *out = rowinfo + tile * (long long)(kRows * kRowTile) + lane;
-        if (n > 0) {
-            out[0] = (uint32_t)(u * g) << kRowFShift;                          // F[0]
-            out[(long long)n * kRowTile] = (uint32_t)(d * g) << kRowGShift;    // G[n]: row 0 of the reversed problem
-        }
+        uint32_t *out_hi = out + (long long)((n + 1) >> 1) * kRowTile;      // row st of the first step with 2 st >= n
+        uint32_t *out_lo = out + (long long)(n >> 1) * kRowTile;            // row n - st of that step
         const uint32_t gdup = dup16((uint32_t)g);
         uint32_t border = 0;
         int rup = INT32_MIN / 2;
+        // a lane past its own last row keeps stepping with its last row's codes: whatever it computes is never stored
+        // (idle lanes, n == 0, may carry any lo: they read row 1, zeroed above)
+        uint32_t pf = code_addr + (uint32_t)((n > 0 ? lo : 0) + 1) * kRowTile;
+        uint32_t pg = code_addr + (uint32_t)(n > 0 ? lo + n : 1) * kRowTile;
         for (int st = 1; st <= nmax; ++st) {
-            const int cf = st <= n ? s_code[(lo + st) * kRowTile + lane] : 0;
-            const int cg = st <= n ? s_code[(lo + n - st + 1) * kRowTile + lane] : 0;
-            const uint4 *pf = (const uint4 *)(tabF + cf * NCOL);
-            const uint4 *pg = (const uint4 *)(tabG + cg * NCOL);
+            const uint32_t cf = lds_u8(pf), cg = lds_u8(pg);
+            if (st < n) { pf += kRowTile; pg -= kRowTile; }
             uint32_t diag = border;
             border += gdup;
             uint32_t left = border - (st == n ? ((uint32_t)g << 16) : 0u);      // G's left border at its last row is -g
             uint32_t tt[NCOL];
+            if (PAIR) {
+                const uint32_t pe = tab_addr + (cf * nc + cg) * (NCOL * 4);
 #pragma unroll
-            for (int c = 0; c < NCOL; c += 4) {
-                const uint4 ef = pf[c >> 2], eg = pg[c >> 2];
-                tt[c] = (c == 0 ? diag : Wc[c - 1]) + ef.x + eg.x;
-                tt[c + 1] = Wc[c] + ef.y + eg.y;
-                tt[c + 2] = Wc[c + 1] + ef.z + eg.z;
-                tt[c + 3] = Wc[c + 2] + ef.w + eg.w;
+                for (int c = 0; c < NCOL; c += 4) {
+                    const uint4 e = lds128(pe + c * 4);
+                    tt[c] = (c == 0 ? diag : Wc[c - 1]) + e.x;
+                    tt[c + 1] = Wc[c] + e.y;
+                    tt[c + 2] = Wc[c + 1] + e.z;
+                    tt[c + 3] = Wc[c + 2] + e.w;
+                }
+            } else {
+                const uint32_t pfa = tab_addr + cf * (NCOL * 4), pga = tab_addr + (nc + cg) * (NCOL * 4);
+#pragma unroll
+                for (int c = 0; c < NCOL; c += 4) {
+                    const uint4 ef = lds128(pfa + c * 4), eg = lds128(pga + c * 4);
+                    tt[c] = (c == 0 ? diag : Wc[c - 1]) + ef.x + eg.x;
+                    tt[c + 1] = Wc[c] + ef.y + eg.y;
+                    tt[c + 2] = Wc[c + 1] + ef.z + eg.z;
+                    tt[c + 3] = Wc[c + 2] + ef.w + eg.w;
+                }
             }
 #pragma unroll
             for (int c = 0; c < NCOL; ++c) {
@@ -154,13 +210,18 @@ k_context(FastDev f, DevTables t, const uint32_t *__restrict__ ctx_tab, const ui
                 Wc[c] = left;
             }
             if (st <= n) {
-                const uint32_t fword = rowinfo_code(cf) | ((left & 0xffffu) << kRowFShift), gword = (left >> 16) << kRowGShift;
-                uint32_t *pf_out = out + (long long)st * kRowTile, *pg_out = out + (long long)(n - st) * kRowTile;
-                if (2 * st < n) { *pf_out = fword; *pg_out = gword; }
-                else if (2 * st == n) { *pf_out = fword | gword; }
-                else { *pf_out |= fword; *pg_out |= gword; }
-            }
-            if (__any_sync(0xffffffffu, st == n)) {
+                // this step's values: F[st] (with the base code of row st, as its profile-row offset code * 144) and
+                // G[n - st].  While 2 st <= n both wait in shared memory for their partners; from 2 st >= n on the
+                // partners are there (for 2 st == n: the word just written) and two finished rows go out.
+                const uint32_t word = cf * 144u + ((left & 0xffffu) << kRowFShift) + ((left >> 16) << kRowGShift);
+                if (2 * st <= n) sts32(early_addr + (uint32_t)st * (kRowTile * 4), word);
+                if (2 * st >= n) {
+                    const uint32_t e = lds32(early_addr + (uint32_t)(n - st) * (kRowTile * 4));   // code | F[n - st], G[st]
+                    *out_hi = (word & kLowMask) | (e & ~kLowMask);
+                    *out_lo = (e & kLowMask) | (word & ~kLowMask);
+                    out_hi += kRowTile;
+                    out_lo -= kRowTile;
+                }
                 if (st == n) {
 #pragma unroll
                     for (int c = 0; c < NCOL; ++c) {
@@ -191,18 +252,35 @@ __device__ __forceinline__ void store_pair_scores(const uint32_t (&Wc)[kCore], u
     if (2 * pr + 1 < G.nb) dst[2 * pr + 1] = s1;
 }
 
-__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+// ---- bulk asynchronous copies (TMA's 1-D form: cp.async.bulk, completion counted on an mbarrier) --------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 
-__device__ __forceinline__ uint4 lds128(uint32_t addr)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 // Lane = window x two barcodes (u16 halves); warp = 32 windows x one barcode pair; profile rows via multicast LDS.
@@ -210,23 +288,46 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr)
 // clock per SM), so the row loop is written to need as few instructions as possible around the 48 essential ones:
 // one LOP3 for the profile address (see kRowCodeMask), a pointer-compare loop, diagonal terms issued one column ahead
 // of the in-place max chain so that no register copies are needed.
-__global__ void __launch_bounds__(kBarcodeWarps * 32, 3)
+// Row-info tiles are double buffered: while the warps work on tile k, warp 0 has the tile the CTA takes next brought
+// into the other buffer by one bulk asynchronous copy (cp.async.bulk, completion on an mbarrier) and publishes its slot
+// metadata next to it, so a tile switch costs one __syncthreads() and no exposed global-memory latency.
+// CTA shape, measured on B200 (profiles/r02_barcode_shapes.txt; PBC096 / NBD104 / dual, ms per 262 144 reads):
+// 8 warps x 2 CTAs at <= 128 registers 10.52 / 1.32 / 4.96; 12 x 1 at 139 registers 10.65 / 1.30 / 5.05; 16 x 1 at 127
+// 10.55 / 1.32 / 5.11; 12 x 2 at 80 registers 10.86 / 1.37 / 5.24 (ptxas pays for the 80-register cap with 5 - 9 register
+// copies per row).  The kernel sits on the shared-memory gather limit either way; fewer, fatter warps win by a little.
+#ifndef QCB_BC_MAXWARPS
+#define QCB_BC_MAXWARPS 8           // warps per CTA (upper bound; the launch picks a divisor-friendly count <= this)
+#endif
+#ifndef QCB_BC_MINBLOCKS
+#define QCB_BC_MINBLOCKS 2          // CTAs per SM the register allocation is sized for
+#endif
+constexpr int kBarcodeMaxWarps = QCB_BC_MAXWARPS;
+
+struct BarcodeTileSlot {            // per row-tile buffer, written by warp 0
+    int4 meta[kRowTile];            // taskmeta of the tile's 32 slots
+    long long tile;                 // tile index, -1 = no more tiles for this CTA
+    unsigned long long bar;         // mbarrier the bulk copy completes on
+};
+
+__global__ void __launch_bounds__(kBarcodeMaxWarps * 32, QCB_BC_MINBLOCKS)
 k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, int rows_min, int rows_cap, int one_set,
                int smem_profile_bytes, const uint32_t *__restrict__ rowinfo, const int4 *__restrict__ taskmeta,
                int32_t *__restrict__ bc_score)
 {
-    // rows_cap = DP rows (0..n) the shared-memory row tile of this launch holds; a tile is taken when its longest region
-    // satisfies rows_min <= n < rows_cap, so a plan whose regions are almost always short (dual mode) can run them with a
-    // small tile (three CTAs per SM) and leave the rare long ones to a second launch with the full tile.
+    // rows_cap = DP rows (0..n) one shared-memory row tile of this launch holds; a tile is taken when its longest region
+    // satisfies rows_min <= n < rows_cap, so a plan whose regions are almost always short (dual mode) can run them with
+    // small tiles (more CTAs per SM) and leave the rare long ones to a second launch with full tiles.
     // one_set = 0: the profiles of all core sets of the plan stay in shared memory (one or two sets: explicit kits, dual).
     // one_set = 1 (many kits, `-k auto`): only the set of the tile at hand is resident -- after the kit vote a chunk's
     // tiles nearly always share one set, so it is loaded once per CTA; a tile that mixes sets runs one pass per set.
     extern __shared__ __align__(1024) uint8_t smem_bc[];
     uint8_t *smem = smem_bc;
     uint32_t *s_prof = (uint32_t *)smem;                             // [pair][code][kProfRowBytes], 1 KB per pair
-    uint32_t *s_row = (uint32_t *)(smem + smem_profile_bytes);       // [kRows][32] row-info words
+    const int tile_bytes = rows_cap * kRowTile * 4;
+    uint8_t *s_rows = smem + smem_profile_bytes;                     // two row tiles: [2][rows_cap][32] row-info words
+    BarcodeTileSlot *s_slot = (BarcodeTileSlot *)(s_rows + 2 * tile_bytes);
     const uint32_t prof_addr = (uint32_t)__cvta_generic_to_shared(s_prof);
-    const uint32_t row_addr = (uint32_t)__cvta_generic_to_shared(s_row);
+    const uint32_t rows_addr = (uint32_t)__cvta_generic_to_shared(s_rows);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -238,21 +339,69 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
     const long long n_tiles = (n_tasks + kRowTile - 1) / kRowTile;
     const int g = f.gap;
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        __syncthreads();                       // previous tile fully consumed (and the profile copy above is complete)
-        const long long task = tile * kRowTile + lane;
-        int4 meta = make_int4(0, 0, 0, 0);
-        if (task < n_tasks) meta = taskmeta[task];
+    if (threadIdx.x == 0) {
+        mbar_init((uint32_t)__cvta_generic_to_shared(&s_slot[0].bar), 1);
+        mbar_init((uint32_t)__cvta_generic_to_shared(&s_slot[1].bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // warp 0: find the next tile of this CTA at or after `cand` that this launch takes, start its bulk copy into buffer
+    // b and publish its metadata; returns the candidate after it.  meta_c = taskmeta of `cand` (loaded by the caller).
+    auto fetch = [&](long long cand, int4 meta_c, int b) -> long long {
+        for (;;) {
+            if (cand >= n_tiles) {
+                if (lane == 0) s_slot[b].tile = -1;
+                return cand;
+            }
+            const int n_c = meta_c.y < 0 ? 0 : meta_c.x;
+            const int nmax_c = __reduce_max_sync(0xffffffffu, n_c);
+            if (nmax_c >= rows_min && nmax_c < rows_cap) {
+                s_slot[b].meta[lane] = meta_c;
+                if (lane == 0) {
+                    s_slot[b].tile = cand;
+                    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_slot[b].bar);
+                    const uint32_t bytes = (uint32_t)(nmax_c + 1) * kRowTile * 4;
+                    mbar_expect_tx(bar, bytes);
+                    bulk_load(rows_addr + (uint32_t)(b * tile_bytes), rowinfo + cand * (long long)(kRows * kRowTile), bytes, bar);
+                }
+                return cand + gridDim.x;
+            }
+            cand += gridDim.x;                                       // not for this launch: look at the next one
+            if (cand < n_tiles) {
+                const long long slot = cand * kRowTile + lane;
+                meta_c = slot < n_tasks ? taskmeta[slot] : make_int4(0, -1, 0, 0);
+            }
+        }
+    };
+    auto load_meta = [&](long long tile) -> int4 {
+        const long long slot = tile * kRowTile + lane;
+        return (tile < n_tiles && slot < n_tasks) ? taskmeta[slot] : make_int4(0, -1, 0, 0);
+    };
+
+    long long cand = blockIdx.x;               // warp 0: the next tile index to look at
+    int4 meta_next = make_int4(0, -1, 0, 0);   // warp 0: its taskmeta, loaded one tile ahead of its use
+    if (warp == 0) {
+        cand = fetch(cand, load_meta(cand), 0);
+        meta_next = load_meta(cand);
+    }
+    __syncthreads();
+
+    for (unsigned it = 0;; ++it) {
+        const int b = (int)(it & 1);
+        const long long tile = s_slot[b].tile;
+        if (tile < 0) break;
+        // buffer b ^ 1 was last read in the previous iteration, which every warp has left: refill it
+        if (warp == 0) {
+            cand = fetch(cand, meta_next, b ^ 1);
+            meta_next = load_meta(cand);
+        }
+        const int4 meta = s_slot[b].meta[lane];
+        mbar_wait((uint32_t)__cvta_generic_to_shared(&s_slot[b].bar), (it >> 1) & 1u);
+        const uint32_t row_addr = rows_addr + (uint32_t)(b * tile_bytes);
+        const uint32_t *s_row = (const uint32_t *)(s_rows + b * tile_bytes);
         const FastGroup G = f.groups[meta.y < 0 ? 0 : meta.y];
         const int n_task = meta.y < 0 ? 0 : meta.x;
-        const int nmax_tile = __reduce_max_sync(0xffffffffu, n_task);
-        if (__syncthreads_or(nmax_tile >= rows_min && nmax_tile < rows_cap) == 0) continue;   // nothing here for this launch
-        {
-            const uint32_t *src = rowinfo + tile * (long long)(kRows * kRowTile);
-            const int words = (nmax_tile + 1) * kRowTile;
-            for (int i = threadIdx.x; i < words; i += blockDim.x) s_row[i] = src[i];
-        }
-        __syncthreads();
         long long w; int k;
         decode_task((long long)(uint32_t)meta.w, n_windows, dual, w, k);      // the task behind this slot
         const int rup = meta.z;
@@ -329,5 +478,6 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
                 }
             }
         }
+        __syncthreads();                       // every warp is done with buffer b; warp 0's slot b ^ 1 is published
     }
 }

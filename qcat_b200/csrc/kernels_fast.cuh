@@ -29,7 +29,6 @@ constexpr int kProfWords = 36;            // words per (pair, code) profile row:
 constexpr int kProfPairBytes = 1024;      // one pair's profile block (<= 7 codes x 144 B), 1 KB aligned: see kRowCodeMask
 constexpr int kRows = kFastMaxStride + 1; // DP rows 0..160
 constexpr int kTile = 32;                 // windows per tile (one per lane)
-constexpr int kBarcodeWarps = 8;
 constexpr int kMaxCtx = 16;               // longest shared prefix / suffix handled by the prologue
 constexpr int kMaxFastGroups = 64;
 
@@ -53,7 +52,7 @@ struct FastDev {
 
 struct AdapterClass {        // the templates of one length class (NC register columns), two per lane
     int nc_cols = 0, npairs = 0, row_words = 0;
-    size_t profile_bytes = 0;    // profile words; followed by npairs int4 {len lo, len hi, output slot lo, output slot hi (-1: none)}
+    size_t profile_bytes = 0;    // profile words; followed by npairs int4 {len lo, len hi, has hi, output slots lo | hi << 16}
     size_t offset = 0;           // byte offset inside AdapterSubset::dev
 };
 
@@ -81,6 +80,7 @@ struct FastPlan {
     int bucket_rows = kRows;         // regions shorter than this go to the front of the task order (k_task_order)
     const uint32_t *ctx_tab = nullptr;   // device: k_context score tables
     int ctx_ncol = 12;
+    bool ctx_pair = true;                // ctx_tab holds one word per (F code, G code, column) instead of two tables
     size_t context_smem = 0;
     void *rowinfo = nullptr;         // [tiles][kRows][32] u32: code row offset | F << 10 | G << 21 (kernels_barcode_fast.cuh)
     void *taskmeta = nullptr;        // [slots] int4 {region length, group, R over prefix columns, task}
@@ -120,8 +120,18 @@ __device__ __forceinline__ uint32_t dup16(uint32_t v) { return v * 0x00010001u; 
 // ---------------------------------------------------------------------------------------------------
 constexpr int kAdapterWarps = 4;
 
+// CTAs per SM the register allocation of each column variant is sized for
+#ifndef QCB_AD48_BLOCKS
+#define QCB_AD48_BLOCKS 6
+#endif
+#ifndef QCB_AD64_BLOCKS
+#define QCB_AD64_BLOCKS 5
+#endif
+#ifndef QCB_AD104_BLOCKS
+#define QCB_AD104_BLOCKS 3
+#endif
 template <int NC>
-__global__ void __launch_bounds__(kAdapterWarps * 32, (NC <= 48 ? 6 : (NC <= 64 ? 5 : 3)))
+__global__ void __launch_bounds__(kAdapterWarps * 32, (NC <= 48 ? QCB_AD48_BLOCKS : (NC <= 64 ? QCB_AD64_BLOCKS : QCB_AD104_BLOCKS)))
 k_adapter_fast(const uint32_t *__restrict__ profile, int profile_words, int row_words, int n_codes,
                const int4 *__restrict__ pair_meta, int npairs,
                const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ wlen, int wshift,
@@ -133,7 +143,13 @@ k_adapter_fast(const uint32_t *__restrict__ profile, int profile_words, int row_
     const int warp = threadIdx.x >> 5;
     uint8_t *s_code = smem + (size_t)profile_words * 4 + (size_t)warp * (kRows * kTile);
     for (int i = threadIdx.x; i < profile_words; i += blockDim.x) s_prof[i] = profile[i];
+    // lanes whose window is shorter than their tile's longest keep stepping through rows they never wrote: make sure
+    // whatever is there is a valid base code from the start
+    for (int i = lane; i < kRows * kTile / 4; i += 32) ((uint32_t *)s_code)[i] = 0u;
     __syncthreads();
+    const uint32_t prof_addr = (uint32_t)__cvta_generic_to_shared(s_prof);
+    const uint32_t code_addr = (uint32_t)__cvta_generic_to_shared(s_code) + lane;
+    const uint32_t row_bytes = (uint32_t)row_words * 4u;
 
     const long long n_tiles = (n_windows + kTile - 1) / kTile;
     const long long n_tasks = n_tiles * npairs;
@@ -141,26 +157,31 @@ k_adapter_fast(const uint32_t *__restrict__ profile, int profile_words, int row_
     for (long long task = (long long)blockIdx.x * kAdapterWarps + warp; task < n_tasks; task += warp_stride) {
         const long long tile = task / npairs;
         const int q = (int)(task % npairs);
-        const int4 meta = pair_meta[q];                 // x = len lo, y = len hi, z / w = output slots (w < 0: no second template)
+        const int4 meta = pair_meta[q];                 // x = len lo, y = len hi, z = has hi, w = output slots (lo | hi << 16)
         const int m_lo = meta.x, m_hi = meta.y;
         const long long w = tile * kTile + lane;
         const bool valid = w < n_windows;
         const int n = valid ? wlen[w >> wshift] : 0;
-        // ---- stage the lane's window codes (low nibble = adapter-matrix code) into shared memory ----
+        // ---- stage the lane's window codes (low nibble = adapter-matrix code) into shared memory; the 3' window of a
+        // read (odd w; wshift = 1) is stored unreversed by k_map_codes: its base p is row n - p of the DP ----
         __syncwarp();
         {
             const uint4 *src = (const uint4 *)(codes + (valid ? w : 0) * stride);
+            const bool rev = wshift && (w & 1);
             for (int ch = 0; ch * 16 < n; ++ch) {
                 uint4 v = src[ch];
                 uint32_t words[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int b = 0; b < 16; ++b)
-                    s_code[(ch * 16 + b + 1) * kTile + lane] = (uint8_t)((words[b >> 2] >> ((b & 3) * 8)) & 15u);
+                for (int b = 0; b < 16; ++b) {
+                    const int p = ch * 16 + b;
+                    const int row = rev ? n - p : p + 1;                 // rows beyond the window (p >= n) are never used
+                    if (row >= 1) s_code[row * kTile + lane] = (uint8_t)((words[b >> 2] >> ((b & 3) * 8)) & 15u);
+                }
             }
         }
         __syncwarp();
         const int nmax = __reduce_max_sync(0xffffffffu, n);
-        const uint32_t *pbase = s_prof + (size_t)q * n_codes * row_words;
+        const uint32_t pbase = prof_addr + (uint32_t)(q * n_codes) * row_bytes;
         uint32_t Wc[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -170,88 +191,106 @@ k_adapter_fast(const uint32_t *__restrict__ profile, int profile_words, int row_
         const uint32_t gdup = dup16((uint32_t)g);
         uint32_t border = 0;                            // (i - 1) * g in both halves
         int best_lo = 0, best_hi = 0;                   // ((W - i g) << 8) | (255 - i), max over rows
-        for (int i = 1; i <= nmax; ++i) {
-            const int code = (i <= n) ? s_code[i * kTile + lane] : 0;
-            const uint4 *prow = (const uint4 *)(pbase + code * row_words);
-            // diagonal terms are formed from the previous row's registers one 4-column chunk ahead of the max chain,
-            // so every Wc register is updated in place (no rotation copies).
-            uint4 e = prow[0];
-            uint32_t t0 = border + e.x;
-            border += gdup;
-            uint32_t left = border;
+        int rowc = 255;                                 // (255 - i) - ((i g) << 8) of the row at hand
+        const int rowc_step = 1 + (g << 8);
+        uint32_t cp = code_addr + kTile;                // row 1
+        int i = 1;
+        while (i <= nmax) {
+            // rows up to the next row at which some lane's window ends run without per-lane branches; a lane's result is
+            // taken at its own last row, so whatever it computes afterwards is never used
+            const int ev = __reduce_min_sync(0xffffffffu, n >= i ? n : INT32_MAX);
+            const uint32_t cp_end = code_addr + (uint32_t)(ev + 1) * kTile;
+            i = ev + 1;
+#pragma unroll 1
+            do {
+                const uint32_t prow = pbase + lds_u8(cp) * row_bytes;
+                cp += kTile;
+                // diagonal terms are formed from the previous row's registers one 4-column chunk ahead of the max chain,
+                // so every Wc register is updated in place (no rotation copies).
+                uint4 e = lds128(prow);
+                uint32_t t0 = border + e.x;
+                border += gdup;
+                uint32_t left = border;
 #pragma unroll
-            for (int c = 0; c < NC; c += 4) {
-                uint4 en = make_uint4(0, 0, 0, 0);
-                if (c + 4 < NC) en = prow[(c >> 2) + 1];
-                const uint32_t t1 = Wc[c] + e.y, t2 = Wc[c + 1] + e.z, t3 = Wc[c + 2] + e.w, t0n = Wc[c + 3] + en.x;
-                left = __vimax3_u16x2(t0, Wc[c], left);     Wc[c] = left;
-                left = __vimax3_u16x2(t1, Wc[c + 1], left); Wc[c + 1] = left;
-                left = __vimax3_u16x2(t2, Wc[c + 2], left); Wc[c + 2] = left;
-                left = __vimax3_u16x2(t3, Wc[c + 3], left); Wc[c + 3] = left;
-                t0 = t0n; e = en;
-            }
-            if (i <= n) {
-                const int rowc = (255 - i) - ((i * g) << 8);
+                for (int c = 0; c < NC; c += 4) {
+                    uint4 en = make_uint4(0, 0, 0, 0);
+                    if (c + 4 < NC) en = lds128(prow + (c + 4) * 4);
+                    const uint32_t t1 = Wc[c] + e.y, t2 = Wc[c + 1] + e.z, t3 = Wc[c + 2] + e.w, t0n = Wc[c + 3] + en.x;
+                    left = __vimax3_u16x2(t0, Wc[c], left);     Wc[c] = left;
+                    left = __vimax3_u16x2(t1, Wc[c + 1], left); Wc[c + 1] = left;
+                    left = __vimax3_u16x2(t2, Wc[c + 2], left); Wc[c + 2] = left;
+                    left = __vimax3_u16x2(t3, Wc[c + 3], left); Wc[c + 3] = left;
+                    t0 = t0n; e = en;
+                }
+                rowc -= rowc_step;
                 best_lo = max(best_lo, (int)(left & 0xffffu) * 256 + rowc);
                 best_hi = max(best_hi, (int)(left >> 16) * 256 + rowc);
-            }
-            if (__any_sync(0xffffffffu, i == n)) {
-                if (i == n) {
-                    int rb_lo = -1, rb_hi = -1;         // ((W - j g) << 8) | (255 - j), max over real columns
+            } while (cp != cp_end);
+            if (n == ev) {
+                int rb_lo = -1, rb_hi = -1;         // ((W - j g) << 8) | (255 - j), max over real columns
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        const int jl = c - (NC - m_lo) + 1, jh = c - (NC - m_hi) + 1;
-                        if (jl >= 1) rb_lo = max(rb_lo, ((int)(Wc[c] & 0xffffu) - jl * g) * 256 + (255 - jl));
-                        if (jh >= 1) rb_hi = max(rb_hi, ((int)(Wc[c] >> 16) - jh * g) * 256 + (255 - jh));
-                    }
+                for (int c = 0; c < NC; ++c) {
+                    const int jl = c - (NC - m_lo) + 1, jh = c - (NC - m_hi) + 1;
+                    if (jl >= 1) rb_lo = max(rb_lo, ((int)(Wc[c] & 0xffffu) - jl * g) * 256 + (255 - jl));
+                    if (jh >= 1) rb_hi = max(rb_hi, ((int)(Wc[c] >> 16) - jh * g) * 256 + (255 - jh));
+                }
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (h == 1 && meta.w < 0) break;
-                        const int m = h ? m_hi : m_lo;
-                        const int best = h ? best_hi : best_lo, rb = h ? rb_hi : rb_lo;
-                        const int C = (best >> 8) - m * g, iC = 255 - (best & 255);
-                        const int R = (rb >> 8) - n * g, jR = 255 - (rb & 255);
-                        int score, end;
-                        if (C > R) { score = C; end = iC - 1; }
-                        else { score = R; end = n - 1; if (jR == m) end = iC - 1; }
-                        const long long o = w * n_subset + (h ? meta.w : meta.z);
-                        ad_score[o] = score;
-                        ad_end[o] = end;
-                    }
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 1 && !meta.z) break;
+                    const int m = h ? m_hi : m_lo;
+                    const int best = h ? best_hi : best_lo, rb = h ? rb_hi : rb_lo;
+                    const int C = (best >> 8) - m * g, iC = 255 - (best & 255);
+                    const int R = (rb >> 8) - n * g, jR = 255 - (rb & 255);
+                    int score, end;
+                    if (C > R) { score = C; end = iC - 1; }
+                    else { score = R; end = n - 1; if (jR == m) end = iC - 1; }
+                    const long long o = w * n_subset + ((pair_meta[q].w >> (16 * h)) & 0xffff);
+                    ad_score[o] = score;
+                    ad_end[o] = end;
                 }
             }
         }
     }
 }
 
-// Window orientation for the packed kernels: ASCII windows (as k_orient) plus one byte per base holding both
-// matrix codes (low nibble adapter matrix, high nibble barcode matrix).
-__global__ void k_orient_codes(const uint8_t *__restrict__ win5, const uint8_t *__restrict__ tail3, int stride,
-                               const int32_t *__restrict__ wlen, long long n_reads, const uint8_t *__restrict__ comp,
-                               const uint8_t *__restrict__ amap, const uint8_t *__restrict__ bmap,
-                               uint8_t *__restrict__ wins, uint8_t *__restrict__ codes)
+// Input bytes -> packed matrix codes for the packed kernels: one byte per base, low nibble = adapter-matrix code, high
+// nibble = barcode-matrix code.  codes[2r] = read[:W] mapped; codes[2r + 1] = read[-W:] mapped through the complement
+// but NOT reversed -- the staging loops of k_adapter_fast / k_context write the bases of odd windows back to front, which
+// costs them nothing, and leaves this pass a pure element-wise map: 16 bytes per thread, coalesced in and out.
+__global__ void k_map_codes(const uint8_t *__restrict__ win5, const uint8_t *__restrict__ tail3, int stride,
+                            const int32_t *__restrict__ wlen, long long n_reads, const uint8_t *__restrict__ comp,
+                            const uint8_t *__restrict__ amap, const uint8_t *__restrict__ bmap, uint8_t *__restrict__ codes)
 {
-    __shared__ uint8_t s_comp[256], s_pack[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_comp[i] = comp[i]; s_pack[i] = (uint8_t)(amap[i] | (bmap[i] << 4)); }
-    __syncthreads();
-    long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per 4 bases
-    const int quads = stride >> 2;
-    if (id >= n_reads * 2 * quads) return;
-    long long w = id / quads;
-    int i0 = (int)(id % quads) * 4;
-    long long r = w >> 1;
-    int len = min(max(wlen[r], 0), stride);
-    uint32_t a = 0, c = 0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        int i = i0 + b;
-        uint8_t v = 0;
-        if (i < len) v = (w & 1) ? s_comp[tail3[r * stride + (len - 1 - i)]] : win5[r * stride + i];
-        a |= (uint32_t)v << (8 * b);
-        c |= (uint32_t)(i < len ? s_pack[v] : 0) << (8 * b);
+    __shared__ uint8_t s_fwd[256], s_rev[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        s_fwd[i] = (uint8_t)(amap[i] | (bmap[i] << 4));
+        const uint8_t c = comp[i];
+        s_rev[i] = (uint8_t)(amap[c] | (bmap[c] << 4));
     }
-    if (wins) ((uint32_t *)wins)[id] = a;
-    ((uint32_t *)codes)[id] = c;
+    __syncthreads();
+    const int vecs = stride >> 4;                                 // 16-byte groups per window slot
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_reads * 2 * vecs) return;
+    const long long w = id / vecs;
+    const int v = (int)(id % vecs);
+    const long long r = w >> 1;
+    const int len = min(max(wlen[r], 0), stride);
+    const uint8_t *tab = (w & 1) ? s_rev : s_fwd;
+    const uint4 in = ((const uint4 *)((w & 1) ? tail3 : win5))[r * vecs + v];
+    const uint32_t src[4] = {in.x, in.y, in.z, in.w};
+    uint32_t dst[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = v * 16 + q * 4 + b;
+            const uint32_t code = i < len ? tab[(src[q] >> (8 * b)) & 255u] : 0u;
+            o |= code << (8 * b);
+        }
+        dst[q] = o;
+    }
+    ((uint4 *)codes)[id] = make_uint4(dst[0], dst[1], dst[2], dst[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -387,23 +426,35 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     std::vector<int32_t> sprime(nc * nc);
     for (int i = 0; i < nc * nc; ++i) sprime[i] = h->bmat[i] + 2 * g;
 
-    // k_context tables: ctx_tab[group][F | G][code][ncol] shifted scores of the shared prefix (low half) and of the
-    // reversed shared suffix (high half), right-aligned in ncol columns, 0 in the dead columns
+    // k_context tables of shifted scores, right-aligned in ncol columns (0 in the dead columns); shared prefix in the low
+    // half, reversed shared suffix in the high half.  Pair form ctx_tab[group][code F][code G][ncol] (one word per cell)
+    // while it stays small, else ctx_tab[group][F | G][code][ncol] (two words per cell).
     int max_ctx = 0;
     for (const FastGroup &G : groups) max_ctx = std::max(max_ctx, std::max(G.u, G.d));
     const int ncol = max_ctx <= 12 ? 12 : 16;
-    std::vector<uint32_t> ctx_tab((size_t)ng * 2 * nc * ncol, 0u);
+    fp.ctx_pair = (size_t)ng * nc * nc * ncol * 4 <= 64 * 1024;
+    const size_t grp_words = (size_t)(fp.ctx_pair ? nc * nc : 2 * nc) * ncol;
+    std::vector<uint32_t> ctx_tab((size_t)ng * grp_words, 0u);
     for (int gi = 0; gi < ng; ++gi) {
         const FastGroup &G = groups[gi];
         for (int code = 0; code < nc; ++code)
             for (int c = 0; c < ncol; ++c) {
                 const int jf = c - (ncol - G.u) + 1, jg = c - (ncol - G.d) + 1;
-                if (jf >= 1) ctx_tab[(((size_t)gi * 2 + 0) * nc + code) * ncol + c] = (uint32_t)sprime[code * nc + ctx[G.up_off + jf - 1]];
-                if (jg >= 1) ctx_tab[(((size_t)gi * 2 + 1) * nc + code) * ncol + c] = (uint32_t)sprime[code * nc + ctx[G.down_off + G.d - jg]] << 16;
+                const uint32_t ef = jf >= 1 ? (uint32_t)sprime[code * nc + ctx[G.up_off + jf - 1]] : 0u;
+                const uint32_t eg = jg >= 1 ? (uint32_t)sprime[code * nc + ctx[G.down_off + G.d - jg]] << 16 : 0u;
+                if (fp.ctx_pair) {
+                    for (int other = 0; other < nc; ++other) {
+                        ctx_tab[(size_t)gi * grp_words + ((size_t)code * nc + other) * ncol + c] |= ef;      // code = F's base
+                        ctx_tab[(size_t)gi * grp_words + ((size_t)other * nc + code) * ncol + c] |= eg;      // code = G's base
+                    }
+                } else {
+                    ctx_tab[(size_t)gi * grp_words + (size_t)code * ncol + c] = ef;
+                    ctx_tab[(size_t)gi * grp_words + (size_t)(nc + code) * ncol + c] = eg;
+                }
             }
     }
     fp.ctx_ncol = ncol;
-    fp.context_smem = ctx_tab.size() * 4 + (size_t)kCtxWarps * kRows * kRowTile;
+    fp.context_smem = ctx_tab.size() * 4 + (size_t)kCtxWarps * (kCtxEarlyRows * kRowTile * 4 + kRows * kRowTile);
     if (fp.context_smem > 200 * 1024) return 0;
 
     // one device slab: profile | groups | ctx_tab
@@ -441,7 +492,7 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     // many sets (`-k auto`: every kit's) keep only the set of the tile at hand in shared memory.
     fp.one_set = profile_bytes > 64 * 1024;
     fp.profile_smem = fp.one_set ? (size_t)fp.max_pairs * kProfPairBytes : profile_bytes;
-    fp.barcode_smem = fp.profile_smem + (size_t)kRows * kRowTile * 4;
+    fp.barcode_smem = fp.profile_smem + 2 * (size_t)kRows * kRowTile * 4 + 2 * sizeof(BarcodeTileSlot);
     if (fp.barcode_smem > 220 * 1024) return 0;
     // Opt every packed kernel into the device's full dynamic shared memory once.  The attribute is a per-device, per-
     // kernel maximum shared by all plans of the process, so it must never be lowered to one plan's own need.
@@ -452,8 +503,10 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
         if ((size_t)optin < fp.barcode_smem || (size_t)optin < fp.context_smem) return 0;
         fp.smem_optin = optin;
         if (cudaFuncSetAttribute(k_barcode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess ||
-            cudaFuncSetAttribute(k_context<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess ||
-            cudaFuncSetAttribute(k_context<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) {
+            cudaFuncSetAttribute(k_context<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess ||
+            cudaFuncSetAttribute(k_context<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess ||
+            cudaFuncSetAttribute(k_context<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess ||
+            cudaFuncSetAttribute(k_context<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) != cudaSuccess) {
             cudaGetLastError();
             return 0;
         }
@@ -493,7 +546,7 @@ inline AdapterSubset *adapter_subset(FastPlan &fp, const int32_t *h_subset, int 
             const int slot_hi = has_hi ? slots[2 * q + 1] : slot_lo;
             const std::vector<uint8_t> &A = fp.a_seq[key[slot_lo]], &B = fp.a_seq[key[slot_hi]];
             meta[q * 4 + 0] = (int)A.size(); meta[q * 4 + 1] = (int)B.size();
-            meta[q * 4 + 2] = slot_lo; meta[q * 4 + 3] = has_hi ? slot_hi : -1;
+            meta[q * 4 + 2] = has_hi ? 1 : 0; meta[q * 4 + 3] = slot_lo | (slot_hi << 16);
             for (int code = 0; code < nc; ++code)
                 for (int c = 0; c < NC; ++c) {
                     int ja = c - (NC - (int)A.size()), jb = c - (NC - (int)B.size());
@@ -530,7 +583,7 @@ inline int launch_adapter_fast(FastPlan &fp, AdapterSubset *sub, const AdapterCl
     }
     const long long n_tiles = (n_windows + kTile - 1) / kTile;
     const long long n_tasks = n_tiles * cls.npairs;
-    int per_sm = NC <= 48 ? 6 : (NC <= 64 ? 5 : 3);
+    int per_sm = NC <= 48 ? QCB_AD48_BLOCKS : (NC <= 64 ? QCB_AD64_BLOCKS : QCB_AD104_BLOCKS);
     while (per_sm > 1 && per_sm * smem > 200 * 1024) --per_sm;
     const int grid = (int)std::min<long long>((n_tasks + kAdapterWarps - 1) / kAdapterWarps, (long long)fp.sm_count * per_sm);
     if (grid <= 0) return 0;
@@ -562,8 +615,8 @@ inline int fast_adapter_stage(FastPlan &fp, const DevTables &, const uint8_t *co
 }
 
 // Shared-context columns of every (window, set) task -> plan-owned rowinfo / taskmeta buffers.
-inline int fast_context_stage(FastPlan &fp, const DevTables &t, const uint8_t *codes, int stride, long long n_windows,
-                              const WindowSel *sel, cudaStream_t st, long long *launches)
+inline int fast_context_stage(FastPlan &fp, const DevTables &t, const uint8_t *codes, int stride, const int32_t *wlen,
+                              long long n_windows, const WindowSel *sel, cudaStream_t st, long long *launches)
 {
     const int dual = t.mode == QCB_MODE_DUAL ? 1 : 0;
     const long long n_tasks = dual ? 2 * n_windows : n_windows;
@@ -601,10 +654,12 @@ inline int fast_context_stage(FastPlan &fp, const DevTables &t, const uint8_t *c
     {
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / fp.context_smem));
         const int cgrid = (int)std::min<long long>((n_tiles + kCtxWarps - 1) / kCtxWarps, (long long)fp.sm_count * per_sm);
-        if (fp.ctx_ncol == 12)
-            k_context<12><<<cgrid, kCtxWarps * 32, fp.context_smem, st>>>(fp.dev, t, fp.ctx_tab, codes, stride, n_windows, sel, dual, perm, rowinfo, taskmeta);
-        else
-            k_context<16><<<cgrid, kCtxWarps * 32, fp.context_smem, st>>>(fp.dev, t, fp.ctx_tab, codes, stride, n_windows, sel, dual, perm, rowinfo, taskmeta);
+#define QCB_LAUNCH_CONTEXT(NCOL, PAIR)                                                                                   \
+    k_context<NCOL, PAIR><<<cgrid, kCtxWarps * 32, fp.context_smem, st>>>(fp.dev, t, fp.ctx_tab, codes, stride, wlen, n_windows, sel, \
+                                                                          dual, perm, rowinfo, taskmeta)
+        if (fp.ctx_ncol == 12) { if (fp.ctx_pair) QCB_LAUNCH_CONTEXT(12, true); else QCB_LAUNCH_CONTEXT(12, false); }
+        else { if (fp.ctx_pair) QCB_LAUNCH_CONTEXT(16, true); else QCB_LAUNCH_CONTEXT(16, false); }
+#undef QCB_LAUNCH_CONTEXT
         ++*launches;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
@@ -621,22 +676,25 @@ inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, long long n_wind
     const uint32_t *rowinfo = (const uint32_t *)fp.rowinfo;
     const int4 *taskmeta = (const int4 *)fp.taskmeta;
     {
-        // warps per CTA: every warp takes one barcode pair per round, so pick the count (<= 8) that wastes the fewest
-        // warp-rounds for this plan's largest set (6 pairs -> 6 warps, 48 pairs -> 8 warps), preferring more warps
-        int warps = kBarcodeWarps, best_waste = 1 << 30;
-        for (int wc = kBarcodeWarps; wc >= 4; --wc) {
+        // warps per CTA: every warp takes one barcode pair per round, so pick the count (<= 12) that wastes the fewest
+        // warp-rounds for this plan's largest set (6 pairs -> 6 warps, 48 pairs -> 12 warps), preferring more warps
+        int warps = kBarcodeMaxWarps, best_waste = 1 << 30;
+        for (int wc = kBarcodeMaxWarps; wc >= 4; --wc) {
             int waste = (fp.max_pairs + wc - 1) / wc * wc - fp.max_pairs;
             if (waste < best_waste) { best_waste = waste; warps = wc; }
         }
-        const size_t regs_per_cta = (size_t)warps * 32 * 80;
+        cudaFuncAttributes attr;
+        if (cudaFuncGetAttributes(&attr, k_barcode_fast) != cudaSuccess) return 1;
+        const size_t regs_per_cta = (size_t)warps * 32 * ((attr.numRegs + 7) / 8 * 8);
         const size_t profile_bytes = fp.profile_smem;
         const int passes = fp.short_rows > 0 ? 2 : 1;
         for (int pass = 0; pass < passes; ++pass) {
             const int rows_min = pass == 0 ? 1 : fp.short_rows;
             const int rows_cap = (passes == 2 && pass == 0) ? fp.short_rows : kRows;
-            const size_t smem = profile_bytes + (size_t)rows_cap * kRowTile * 4;
-            int ctas_per_sm = (int)std::min<size_t>((220 * 1024) / std::max<size_t>(1, smem), 65536 / regs_per_cta);
-            ctas_per_sm = std::max(1, std::min(ctas_per_sm, 8));
+            // shared memory: profile | two row tiles (double buffered) | two tile slots
+            const size_t smem = profile_bytes + 2 * (size_t)rows_cap * kRowTile * 4 + 2 * sizeof(BarcodeTileSlot);
+            int ctas_per_sm = (int)std::min<size_t>((220 * 1024) / std::max<size_t>(1, smem + 1024), 65536 / regs_per_cta);
+            ctas_per_sm = std::max(1, std::min(ctas_per_sm, std::min(8, 2048 / (warps * 32))));
             int grid = (int)std::min<long long>(n_tiles, (long long)fp.sm_count * ctas_per_sm);
             k_barcode_fast<<<grid, warps * 32, smem, st>>>(fp.dev, n_windows, dual, bmax0, bslots, rows_min, rows_cap, fp.one_set ? 1 : 0,
                                                            (int)profile_bytes, rowinfo, taskmeta, bc_score);

@@ -24,8 +24,11 @@ def _targets():
     return [BarcodeScannerEPI2ME, BarcodeScannerDual, BarcodeScannerSimple]
 
 
-def install(device=None):
-    """Patch qcat's scanner classes; `device` pins the CUDA device index for every scanner created afterwards."""
+def install(device=None, devices=None):
+    """Patch qcat's scanner classes; `device` pins the CUDA device index for every scanner created afterwards,
+    `devices` (a list of indices or "all") spreads every batch over several GPUs of this process."""
+    if devices is not None:
+        device = devices
     for cls in _targets():
         if cls in _saved:
             continue

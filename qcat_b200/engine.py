@@ -221,6 +221,97 @@ class DevicePlan(object):
         return base, total + 1
 
 
+class MultiDevicePlan(object):
+    """One DevicePlan per device of this process behind the DevicePlan interface (qcb_detect_multi /
+    qcb_detect_auto_multi): reads are dealt to the devices in blocks, round-robin, every device runs its own copy /
+    compute pipeline on its own host thread, and records land at their reads' positions.  `devices`: CUDA device
+    indices; an index may repeat (two plans sharing one device -- how the sharding is tested on a one-GPU box)."""
+
+    def __init__(self, tables, devices):
+        devices = [int(d) for d in devices]
+        if not devices:
+            raise ValueError("MultiDevicePlan needs at least one device")
+        self.tables = tables
+        self.devices = devices
+        self.plans = [DevicePlan(tables, device=d) for d in devices]
+        self._lib = self.plans[0]._lib
+        self._handles = (ctypes.c_void_p * len(self.plans))(*[p._handle for p in self.plans])
+        self.device = devices[0]
+
+    def close(self):
+        for plan in self.plans:
+            plan.close()
+
+    def info(self):
+        infos = [p.info() for p in self.plans]
+        out = dict(infos[0])
+        out["kernel_launches"] = sum(i["kernel_launches"] for i in infos)
+        out["workspace_bytes"] = sum(i["workspace_bytes"] for i in infos)
+        out["devices"] = list(self.devices)
+        out["kernel_launches_per_device"] = [i["kernel_launches"] for i in infos]
+        return out
+
+    def set_force_generic(self, force):
+        for plan in self.plans:
+            plan.set_force_generic(force)
+
+    @staticmethod
+    def _host_arrays(win5, tail3, wlen, read_len):
+        win5 = np.ascontiguousarray(win5, dtype=np.uint8)
+        tail3 = np.ascontiguousarray(tail3, dtype=np.uint8)
+        wlen = np.ascontiguousarray(wlen, dtype=np.int32)
+        read_len = np.ascontiguousarray(read_len, dtype=np.int64)
+        n = int(wlen.shape[0])
+        stride = int(win5.shape[1]) if win5.ndim == 2 else int(win5.size // max(n, 1))
+        return win5, tail3, wlen, read_len, n, stride
+
+    def detect(self, win5, tail3, wlen, read_len, subset=None, out=None):
+        win5, tail3, wlen, read_len, n, stride = self._host_arrays(win5, tail3, wlen, read_len)
+        if out is None:
+            out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+        sub, nsub = DevicePlan._subset(subset)
+        _ffi.check(self._lib.qcb_detect_multi(self._handles, len(self.plans), _vp(win5), _vp(tail3), stride, _vp(wlen),
+                                              _vp(read_len), n, _vp(sub) if sub is not None else None, nsub, _vp(out)))
+        return out
+
+    def detect_auto(self, win5, tail3, wlen, read_len, kit_of_layout, batch_size, out=None, return_kits=False):
+        win5, tail3, wlen, read_len, n, stride = self._host_arrays(win5, tail3, wlen, read_len)
+        kits = np.ascontiguousarray(kit_of_layout, dtype=np.int32)
+        if kits.size != self.tables.n_layouts:
+            raise ValueError("kit_of_layout needs one entry per layout")
+        if out is None:
+            out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+        batch_kit = np.zeros(max(1, (n + int(batch_size) - 1) // max(int(batch_size), 1)), dtype=np.int32)
+        _ffi.check(self._lib.qcb_detect_auto_multi(self._handles, len(self.plans), _vp(win5), _vp(tail3), stride, _vp(wlen),
+                                                   _vp(read_len), n, _vp(kits), int(batch_size), _vp(out), _vp(batch_kit)))
+        return (out, batch_kit) if return_kits else out
+
+    # calls that are not worth spreading (single windows, the fallback vote) run on the first device
+    def scan_windows(self, windows, subset=None):
+        return self.plans[0].scan_windows(windows, subset)
+
+    def kit_vote(self, win5, tail3, wlen):
+        return self.plans[0].kit_vote(win5, tail3, wlen)
+
+    def histogram_layout(self):
+        return self.plans[0].histogram_layout()
+
+    def hist_allgather(self, d_counts, n_bins, d_gathered):
+        """qcb_hist_allgather: d_counts[d] / d_gathered[d] are device pointers (ints) on device d."""
+        counts = (ctypes.c_void_p * len(self.plans))(*[int(c) for c in d_counts])
+        gathered = (ctypes.c_void_p * len(self.plans))(*[int(g) for g in d_gathered])
+        _ffi.check(self._lib.qcb_hist_allgather(self._handles, len(self.plans), counts, int(n_bins), gathered))
+
+
+def make_plan(tables, device=None):
+    """DevicePlan for one device index (or None = default), MultiDevicePlan for a list / tuple of indices or "all"."""
+    if isinstance(device, str) and device == "all":
+        device = list(range(device_count()))
+    if isinstance(device, (list, tuple)):
+        return MultiDevicePlan(tables, device) if len(device) != 1 else DevicePlan(tables, device=device[0])
+    return DevicePlan(tables, device=device)
+
+
 def microbench_cell_rate(device=None):
     """(packed DP cell updates per second the SMs can issue, effective SM MHz) on this device."""
     cells = ctypes.c_double()

@@ -192,7 +192,8 @@ class _Labels(object):
                 name, bid = "barcode{:02d}/{:02d}".format(b[0].id, b[1].id), "{}/{}".format(b[0].id, b[1].id)
             else:
                 name, bid = b.name, str(b.id)
-            kit = "none" if self.tables.mode == 2 else str(self.tables.layouts[layout_index].kit)   # simple: adapter None
+            # simple mode: the adapter is None and the reference prints just that (cli.py:423-426: kit_name = None)
+            kit = "None" if self.tables.mode == 2 else str(self.tables.layouts[layout_index].kit)
             self.by_key[key] = (self.intern(name), self.intern(bid), self.intern(kit))
         return self.by_key[key]
 

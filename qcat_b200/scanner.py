@@ -50,12 +50,17 @@ def _config_key(cfg):
             size_a, mat_a.tobytes(), map_a.tobytes(), size_b, mat_b.tobytes(), map_b.tobytes())
 
 
+def _device_key(device):
+    return tuple(device) if isinstance(device, (list, tuple)) else device
+
+
 class GpuScannerMixin(object):
     """GPU-backed detect_barcode / detect_barcode_batch / scan for a reference-shaped scanner object
     (attributes used: layouts, min_quality, override_kit_name, barcodes, enable_filter_barcodes,
     scan_middle_adapter, get_name())."""
 
-    device = None            # CUDA device index; None -> QCAT_B200_DEVICE / LOCAL_RANK / 0
+    device = None            # CUDA device index, a list of indices or "all" (one plan per device, reads sharded between
+                             # them inside this process); None -> QCAT_B200_DEVICE / LOCAL_RANK / 0
 
     # ---- plan management ------------------------------------------------------------------------
 
@@ -69,22 +74,22 @@ class GpuScannerMixin(object):
         mode = self._mode_name()
         override = getattr(self, "barcodes", None)
         if mode == "simple":
-            key = ("simple", tuple(override or ()), _config_key(qcat_config), float(self.min_quality), self.device)
+            key = ("simple", tuple(override or ()), _config_key(qcat_config), float(self.min_quality), _device_key(self.device))
             return key, lambda: Tables.simple(override, qcat_config, self.min_quality)
         layouts = self.layouts if layouts is None else layouts
         key = (tuple(id(l) for l in layouts), _config_key(qcat_config), float(self.min_quality),
-               None if not override else tuple(override), mode, self.device)
+               None if not override else tuple(override), mode, _device_key(self.device))
         return key, lambda: Tables(layouts, qcat_config, mode, self.min_quality, override)
 
     def _plan_for(self, qcat_config, layouts=None):
-        from qcat_b200.engine import DevicePlan
+        from qcat_b200.engine import make_plan
         key, make_tables = self._tables_for(qcat_config, layouts)
         cache = self.__dict__.setdefault("_qcb_plans", {})
         plan = cache.get(key)
         if plan is None:
             if len(cache) >= 4:
                 cache.pop(next(iter(cache))).close()
-            plan = cache[key] = DevicePlan(make_tables(), device=self.device)
+            plan = cache[key] = make_plan(make_tables(), device=self.device)
         return plan
 
     def _subset_for(self, plan, kits):
