@@ -355,12 +355,16 @@ class Workload(object):
             sampler.start()
             time.sleep(0.3)
         self.barrier()
+        if self.world > 1:
+            # align the ranks on the device as well: this tiny collective ends at the same moment on every GPU, and the
+            # start event is recorded right behind it (host-side launch skew between the ranks stays out of the region)
+            import torch.distributed as dist
+            dist.all_reduce(torch.zeros(1, device=self.dev))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             self.step()
         if self.world > 1:
-            import torch.distributed as dist
             gathered = [torch.zeros_like(self.d_counts) for _ in range(self.world)]
             dist.all_gather(gathered, self.d_counts)          # the path's only collective: per-barcode counts, once
             total_counts = torch.stack(gathered).sum(0)

@@ -68,6 +68,7 @@ struct qcb_plan {
     void *slab = nullptr;            // device tables
     size_t slab_bytes = 0;
     std::vector<int32_t> h_group_off, h_group, h_tmpl_off, h_adapter_off;
+    std::vector<int32_t> subset_cached;   // layout subset currently held in subset_dev
     int bmax0 = 0, bmax1 = 0;        // largest barcode set 0 / set 1 over all layouts
     int max_adapter = 0, max_template = 0;
     FastPlan fast;                   // packed-kernel tables (kernels_fast.cuh)
@@ -386,9 +387,12 @@ int prepare_subset(qcb_plan *p, const int32_t *subset, int n_subset, std::vector
         for (int v : h)
             if (v < 0 || v >= p->t.n_layouts) return fail("layout subset entry %d out of range", v);
     }
+    if (h == p->subset_cached && p->subset_dev.ptr) return 0;    // same subset as the previous call: already on the device
     if (p->subset_dev.reserve(h.size() * 4)) return 1;
-    QCB_CUDA(cudaMemcpyAsync(p->subset_dev.ptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
-    // the host vector must outlive the async copy: pageable memcpy is staged synchronously by the runtime.
+    // a change of subset is rare (another kit): wait for whatever may still read the old one, on any stream
+    QCB_CUDA(cudaDeviceSynchronize());
+    QCB_CUDA(cudaMemcpy(p->subset_dev.ptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    p->subset_cached = h;
     return 0;
 }
 
@@ -513,10 +517,19 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
         if (p->auto_kit.reserve((size_t)n_batches * 4)) return 1;
     }
     // the chunks of this call: the whole input, or this device's blocks of a multi-device call
+    // The first two chunks are a quarter and a half of the regular size: the pipeline starts computing sooner.
     std::vector<std::pair<long long, long long>> chunks;
+    const long long unit = auto_mode ? batch_size : 32;
     for (long long base = shard ? shard->first : 0; base < n_reads; base += shard ? shard->period : n_reads) {
         const long long end = std::min<long long>(n_reads, base + span);
-        for (long long off = base; off < end; off += chunk) chunks.emplace_back(off, std::min<long long>(chunk, end - off));
+        for (long long off = base; off < end;) {
+            long long size = chunk;
+            if (chunks.size() < 2 && chunk >= (1 << 16))
+                size = std::max<long long>(unit, (chunk >> (2 - chunks.size())) / unit * unit);
+            size = std::min<long long>(size, end - off);
+            chunks.emplace_back(off, size);
+            off += size;
+        }
     }
     const size_t out_item = vote ? 4 : sizeof(qcb_result);
     int rc = 0;

@@ -139,7 +139,7 @@ k_context(FastDev f, DevTables t, const uint32_t *__restrict__ ctx_tab, const ui
             const uint4 *src = (const uint4 *)(codes + w * stride);
             const int wl = wlen[w >> 1];
             const bool rev = (w & 1) != 0;
-            const int first = n > 0 ? (rev ? wl - (lo + n) : 0) : 0, last = n > 0 ? (rev ? wl - lo : lo + n) : 0;
+            const int first = n > 0 ? (rev ? wl - (lo + n) : lo) : 0, last = n > 0 ? (rev ? wl - lo : lo + n) : 0;
             for (int ch = max(first, 0) >> 4; ch * 16 < last; ++ch) {
                 const uint4 v = src[ch];
                 const uint32_t words[4] = {v.x, v.y, v.z, v.w};
@@ -312,7 +312,7 @@ struct BarcodeTileSlot {            // per row-tile buffer, written by warp 0
 __global__ void __launch_bounds__(kBarcodeMaxWarps * 32, QCB_BC_MINBLOCKS)
 k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, int rows_min, int rows_cap, int one_set,
                int smem_profile_bytes, const uint32_t *__restrict__ rowinfo, const int4 *__restrict__ taskmeta,
-               int32_t *__restrict__ bc_score)
+               int32_t *__restrict__ bc_score, const unsigned int *__restrict__ bucket_counts, int pass)
 {
     // rows_cap = DP rows (0..n) one shared-memory row tile of this launch holds; a tile is taken when its longest region
     // satisfies rows_min <= n < rows_cap, so a plan whose regions are almost always short (dual mode) can run them with
@@ -336,8 +336,12 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
     int resident = -1;                         // one_set: byte offset of the core set whose profile is in shared memory
 
     const long long n_tasks = dual ? 2 * n_windows : n_windows;
-    const long long n_tiles = (n_tasks + kRowTile - 1) / kRowTile;
     const int g = f.gap;
+    // Two-launch plans (pass 0 = short regions, pass 1 = long ones): k_task_order put the short tasks in the first
+    // bucket_counts[0] slots and the long ones in the last bucket_counts[1], so each launch only walks its own tiles.
+    long long tile_begin = 0, n_tiles = (n_tasks + kRowTile - 1) / kRowTile;
+    if (pass == 0) n_tiles = min(n_tiles, ((long long)bucket_counts[0] + kRowTile - 1) / kRowTile);
+    if (pass == 1) tile_begin = (n_tasks - (long long)bucket_counts[1]) / kRowTile;
 
     if (threadIdx.x == 0) {
         mbar_init((uint32_t)__cvta_generic_to_shared(&s_slot[0].bar), 1);
@@ -379,7 +383,7 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
         return (tile < n_tiles && slot < n_tasks) ? taskmeta[slot] : make_int4(0, -1, 0, 0);
     };
 
-    long long cand = blockIdx.x;               // warp 0: the next tile index to look at
+    long long cand = tile_begin + blockIdx.x;  // warp 0: the next tile index to look at
     int4 meta_next = make_int4(0, -1, 0, 0);   // warp 0: its taskmeta, loaded one tile ahead of its use
     if (warp == 0) {
         cand = fetch(cand, load_meta(cand), 0);

@@ -696,8 +696,10 @@ inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, long long n_wind
             int ctas_per_sm = (int)std::min<size_t>((220 * 1024) / std::max<size_t>(1, smem + 1024), 65536 / regs_per_cta);
             ctas_per_sm = std::max(1, std::min(ctas_per_sm, std::min(8, 2048 / (warps * 32))));
             int grid = (int)std::min<long long>(n_tiles, (long long)fp.sm_count * ctas_per_sm);
+            const unsigned int *bucket_counts = (const unsigned int *)((const uint8_t *)fp.perm + (size_t)n_tiles * kRowTile * 4);
             k_barcode_fast<<<grid, warps * 32, smem, st>>>(fp.dev, n_windows, dual, bmax0, bslots, rows_min, rows_cap, fp.one_set ? 1 : 0,
-                                                           (int)profile_bytes, rowinfo, taskmeta, bc_score);
+                                                           (int)profile_bytes, rowinfo, taskmeta, bc_score, bucket_counts,
+                                                           passes == 2 ? pass : -1);
             ++*launches;
         }
     }
