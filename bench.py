@@ -103,15 +103,17 @@ def make_scanner_tables(spec):
     return sc, Tables(sc.layouts, config.qcatConfig(), spec["mode"], sc.min_quality)
 
 
-def synth_batch(spec, sc, n, unique, seed):
-    """n reads for one rank and step: `unique` distinct reads (all of them unless --unique-reads says otherwise)."""
+def synth_batch(spec, sc, n, unique, seed, world=1):
+    """n reads for one rank and step: `unique` distinct reads (all of them unless --unique-reads says otherwise).
+    The generator's worker processes share the host cores with the other ranks' workers."""
     from qcat_b200 import scanner, synth
     foreign = scanner.BarcodeScannerEPI2ME(kit="RBK001").layouts
     layouts = sc.layouts
     if spec.get("source_kit"):                         # auto-kit workload: reads of one kit, scanner knows them all
         layouts = scanner.BarcodeScannerEPI2ME(kit=spec["source_kit"]).layouts
     u = n if unique <= 0 else min(n, unique)
-    d = synth.generate_parallel(layouts, u, seed=seed, foreign_layouts=foreign, **spec.get("gen", {}))
+    workers = max(2, (os.cpu_count() or 2) // max(world, 1))
+    d = synth.generate_parallel(layouts, u, seed=seed, workers=workers, foreign_layouts=foreign, **spec.get("gen", {}))
     out = {}
     for k in ("win5", "tail3", "wlen", "read_len"):
         out[k] = d[k] if u == n else np.ascontiguousarray(np.concatenate([d[k]] * ((n + u - 1) // u), axis=0)[:n])
@@ -280,7 +282,7 @@ class Workload(object):
         t0 = time.perf_counter()
         # global read i of a step belongs to rank i % world (round-robin): rank r draws shard r
         self.batch, self.unique = synth_batch(self.spec, self.sc, self.n, args.unique_reads,
-                                              seed=[20261017, self.spec["index"], rank])
+                                              seed=[20261017, self.spec["index"], rank], world=world)
         self.gen_s = time.perf_counter() - t0
         self.stride = int(self.batch["win5"].shape[1])
         self.names = [l.kit for l in self.sc.layouts]
@@ -528,7 +530,7 @@ def sharded_parity(w, n_common=65539):
     from qcat_b200 import dist as qdist
     from tests import helpers
     torch = w.torch
-    common, _ = synth_batch(w.spec, w.sc, n_common, 0, seed=[20261017, 99])
+    common, _ = synth_batch(w.spec, w.sc, n_common, 0, seed=[20261017, 99], world=w.world)
     idx = qdist.shard_indices(n_common, w.rank, w.world)
     mine = w.plan.detect(common["win5"][idx], common["tail3"][idx], common["wlen"][idx], common["read_len"][idx])
     per = (n_common + w.world - 1) // w.world
@@ -587,9 +589,9 @@ def strong_scaling(w, total_reads):
             "data": "each rank streams its share as passes over its %d unique reads" % w.unique}
 
 
-def measure_extra(name, args, rank, world, torch, dev, local_rank):
+def measure_extra(w, args, rank, world, torch, dev, local_rank):
     """One of the non-headline BASELINE configs: device-resident rate, e2e, stage times, parity spot check."""
-    w = Workload(name, args, rank, world)
+    name = w.name
     w.to_device(torch, dev, local_rank)
     try:
         elapsed_ms, _, launches = w.timed(args.extra_steps, 3)
@@ -630,7 +632,9 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     # the synthetic shard is drawn by forked numpy workers: before this process touches CUDA
     head = Workload(args.workload, args, rank, world)
-    log("rank %d: %d reads generated in %.1f s" % (rank, head.n, head.gen_s))
+    extra_names = [x for x in args.extra_workloads.split(",") if x and x != args.workload]
+    extra = [Workload(name, args, rank, world) for name in extra_names]
+    log("rank %d: %d workloads x %d reads generated in %.1f s" % (rank, 1 + len(extra), head.n, head.gen_s + sum(w.gen_s for w in extra)))
 
     import torch
     import torch.distributed as dist
@@ -680,11 +684,11 @@ def run_ours(args):
 
     # ---- the other BASELINE configs -------------------------------------------------------------------------
     extras = {}
-    for name in [x for x in args.extra_workloads.split(",") if x]:
-        if name == args.workload:
-            continue
+    for w in extra:
+        name = w.name
         try:
-            extras[name] = measure_extra(name, args, rank, world, torch, dev, local_rank)
+            extras[name] = measure_extra(w, args, rank, world, torch, dev, local_rank)
+            w.batch = None                                        # host copy no longer needed
             if rank == 0:
                 log("%s: %.2f M reads/s" % (name, extras[name]["value"] / 1e6))
         except Exception as exc:                                # noqa: BLE001 -- reported, the headline stands

@@ -342,6 +342,7 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
     long long tile_begin = 0, n_tiles = (n_tasks + kRowTile - 1) / kRowTile;
     if (pass == 0) n_tiles = min(n_tiles, ((long long)bucket_counts[0] + kRowTile - 1) / kRowTile);
     if (pass == 1) tile_begin = (n_tasks - (long long)bucket_counts[1]) / kRowTile;
+    if (tile_begin + blockIdx.x >= n_tiles) return;           // nothing for this CTA (before it loads any profile)
 
     if (threadIdx.x == 0) {
         mbar_init((uint32_t)__cvta_generic_to_shared(&s_slot[0].bar), 1);

@@ -68,6 +68,12 @@ def main():
     fastx.demux_file(path, auto, keep_records=False)
     dt = time.perf_counter() - t0
     out["demux_auto_kit"] = {"reads_per_s": n / dt, "gb_per_s": size / 1e9 / dt}
+    out["demux_auto_kit_by_chunk_mb"] = {}
+    for mb in (64, 128, 256):
+        t0 = time.perf_counter()
+        fastx.demux_file(path, auto, keep_records=False, chunk_bytes=mb << 20)
+        dt = time.perf_counter() - t0
+        out["demux_auto_kit_by_chunk_mb"][str(mb)] = size / 1e9 / dt
     print(json.dumps(out))
     os.remove(path)
 
