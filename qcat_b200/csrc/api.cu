@@ -475,13 +475,14 @@ int detect_device_impl(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail
 // One device's share of a multi-device call: blocks of `block` reads starting at first, first + period, ...
 struct Shard { long long first, block, period; };
 
-int validate_wlen(const qcb_plan *p, const int32_t *wlen, int64_t n_reads, int32_t stride, bool window_mode)
+int validate_wlen(const qcb_plan *p, const int32_t *wlen, int64_t n_reads, int32_t stride, bool window_mode, int64_t first = 0)
 {
-    for (int64_t i = 0; i < n_reads; ++i) {
-        const int32_t len = wlen[i];
-        if (len < 0 || len > stride || (!window_mode && len > p->t.W))
-            return fail("wlen[%lld] = %d outside [0, %d]", (long long)i, len, window_mode ? stride : std::min<int>(stride, p->t.W));
-    }
+    const int32_t limit = window_mode ? stride : std::min<int>(stride, p->t.W);
+    uint32_t bad = 0;
+    for (int64_t i = 0; i < n_reads; ++i) bad |= (uint32_t)(wlen[i] < 0) | (uint32_t)(wlen[i] > limit);   // branch-free: vectorises
+    if (!bad) return 0;
+    for (int64_t i = 0; i < n_reads; ++i)
+        if (wlen[i] < 0 || wlen[i] > limit) return fail("wlen[%lld] = %d outside [0, %d]", (long long)(first + i), wlen[i], limit);
     return 0;
 }
 
@@ -498,7 +499,7 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
     if (n_reads == 0) return 0;
     const bool window_mode = tail3 == nullptr;
     if (!win5 || !wlen || (!vote && !out) || (!vote && !window_mode && !read_len)) return fail("NULL input/output buffer");
-    if (!shard && validate_wlen(p, wlen, n_reads, stride, window_mode)) return 1;
+    // (window lengths are validated chunk by chunk, right before a chunk is copied: off the critical path of a large call)
     QCB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = p->stream, s_in = p->copy_in, s_out = p->copy_out;
     // Pipeline granularity: at least 64 Ki reads per chunk (small kernels lose time in their last wave of tiles), larger
@@ -557,6 +558,7 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
         }
         uint8_t *d = (uint8_t *)p->in_stage2[b].ptr;
         void *d_res = p->out_stage2[b].ptr;
+        if (validate_wlen(p, wlen + off, n, stride, window_mode, off)) { rc = 1; break; }
         LOOP_CUDA(cudaMemcpyAsync(d, win5 + off * stride, b_win, cudaMemcpyHostToDevice, s_in));
         if (!window_mode) { LOOP_CUDA(cudaMemcpyAsync(d + o_tail, tail3 + off * stride, b_win, cudaMemcpyHostToDevice, s_in)); }
         LOOP_CUDA(cudaMemcpyAsync(d + o_len, wlen + off, b_len, cudaMemcpyHostToDevice, s_in));
@@ -815,7 +817,6 @@ static int detect_multi_impl(qcb_plan *const *plans, int32_t n_plans, const uint
     if (n_reads == 0) return 0;
     if (!win5 || !tail3 || !wlen || !read_len || !out) return fail("NULL input/output buffer");
     if (kit_of_layout && batch_size <= 0) return fail("batch_size must be positive");
-    if (validate_wlen(plans[0], wlen, n_reads, stride, false)) return 1;
     // block size: ~4 blocks per device for load balance, at least 64 Ki reads, whole CLI batches in auto-kit calls
     long long block = std::max<long long>(1 << 16, (n_reads / (4LL * n_plans) + 31) / 32 * 32);
     if (kit_of_layout) block = std::max<long long>(1, (block + batch_size - 1) / batch_size) * batch_size;

@@ -178,3 +178,25 @@ def test_plans_of_different_kits_coexist():
             helpers.assert_records_equal(got, want, "interleaved plans")
     for plan, _, _ in made:
         plan.close()
+
+
+def test_host_entry_points_reject_bad_window_lengths():
+    """Window lengths are validated chunk by chunk on the host path: a bad entry deep inside a large call fails the call
+    with its index, and the plan stays usable."""
+    from qcat_b200 import _ffi, config, engine, scanner, synth
+    from qcat_b200.tables import Tables
+    sc = scanner.BarcodeScannerEPI2ME(kit="NBD103/NBD104")
+    tables = Tables(sc.layouts, config.qcatConfig(), "epi2me", sc.min_quality)
+    data = synth.generate(sc.layouts, 150000, seed=8)
+    plan = engine.DevicePlan(tables, device=0)
+    try:
+        good = plan.detect(data["win5"], data["tail3"], data["wlen"], data["read_len"])
+        for index, value in ((140000, 151), (7, -1)):
+            wlen = data["wlen"].copy()
+            wlen[index] = value
+            with pytest.raises(_ffi.QcbError, match=r"wlen\[%d\]" % index):
+                plan.detect(data["win5"], data["tail3"], wlen, data["read_len"])
+        again = plan.detect(data["win5"], data["tail3"], data["wlen"], data["read_len"])
+        helpers.assert_records_equal(again, good, "plan reusable after a rejected call")
+    finally:
+        plan.close()
