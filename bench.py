@@ -488,8 +488,8 @@ def compute_roofline(w, step_ms, dom, dom_ms, clocks, local_rank, args):
                "full_window_fraction": full / (2.0 * ncells_sample),
                "achieved": cells_per_read * n / (step_ms * 1e-3),
                "peak": cell_peak,
-               "peak_source": "qcb_microbench_cell_rate: IMAD.IADD + VIMNMX3.U16x2 per 2 cells (the pair in the kernels' "
-                              "SASS, profiles/sass_k_barcode_fast_r02.txt), same box",
+               "peak_source": "qcb_microbench_cell_rate: the pair in the kernels' SASS (IMAD / IMAD.IADD + VIMNMX3.U16x2 per 2 "
+                              "cells, profiles/sass_k_barcode_fast_r02.txt), fastest of three register-operand variants, same box",
                "peak_sm_mhz": load_mhz, "peak_cells_per_clk_per_sm": cells_per_clk / sm_count,
                "peak_warp_inst_per_clk_per_sm": cells_per_clk / sm_count / 32.0}
     compute["frac"] = compute["achieved"] / cell_peak

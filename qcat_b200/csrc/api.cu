@@ -126,6 +126,14 @@ int upload_tables(qcb_plan *p, const qcb_tables *h)
     size_t o_toff = slab_put(slab, h->tmpl_off, nt + 1);
     size_t o_tseq = slab_put(slab, h->tmpl_seq, nt ? h->tmpl_off[nt] : 0);
     size_t o_tid = slab_put(slab, h->tmpl_ident, nt);
+    std::vector<int32_t> group_tlen(ng > 0 ? ng : 1, -1);
+    for (int g = 0; g < ng; ++g) {
+        const int b0 = h->group_off[g], b1 = h->group_off[g + 1];
+        int tl = b1 > b0 ? h->tmpl_off[b0 + 1] - h->tmpl_off[b0] : -1;
+        for (int b = b0; b < b1; ++b) if (h->tmpl_off[b + 1] - h->tmpl_off[b] != tl) tl = -1;
+        group_tlen[g] = tl;
+    }
+    size_t o_gtl = slab_put(slab, group_tlen.data(), ng);
 
     QCB_CUDA(cudaMalloc(&p->slab, slab.size()));
     p->slab_bytes = slab.size();
@@ -147,6 +155,7 @@ int upload_tables(qcb_plan *p, const qcb_tables *h)
     t.is_double = (const int32_t *)(d + o_dbl);
     t.group_off = (const int32_t *)(d + o_goff); t.tmpl_off = (const int32_t *)(d + o_toff);
     t.tmpl_seq = d + o_tseq; t.tmpl_ident = (const int32_t *)(d + o_tid);
+    t.group_tlen = (const int32_t *)(d + o_gtl);
 
     p->h_group_off.assign(h->group_off, h->group_off + ng + 1);
     p->h_group.assign(h->group, h->group + nl * 2);

@@ -407,6 +407,18 @@ __device__ __forceinline__ void pick_barcode(const DevTables &t, int g, int rlen
     best = -1; best_score = 0.0;
     if (rlen <= 0 || g < 0) return;
     int base = t.group_off[g], cnt = t.group_off[g + 1] - base;
+    const int tl_all = t.group_tlen[g];
+    if (tl_all > 0) {
+        // every template of the group has the same length: score * 100.0 / tlen is strictly increasing in the integer
+        // score and is 0.0 exactly for score 0, so the rule can run on the integers and divide once
+        bool have = false; int mx = 0, arg = -1;
+        for (int b = 0; b < cnt; ++b) {
+            const int sc = scores[b];
+            if (!have || mx == 0 || mx < sc) { have = true; mx = sc; arg = b; }
+        }
+        best = arg; best_score = (double)mx * 100.0 / (1.0 * (double)tl_all);
+        return;
+    }
     bool have = false; double mx = 0.0; int arg = -1;
     for (int b = 0; b < cnt; ++b) {
         int tl = t.tmpl_off[base + b + 1] - t.tmpl_off[base + b];

@@ -37,6 +37,7 @@ struct DevTables {
     const int32_t *tmpl_off;
     const uint8_t *tmpl_seq;
     const int32_t *tmpl_ident;
+    const int32_t *group_tlen;   // [n_groups] common template length of the group, -1 if its templates differ in length
 };
 
 // Per-window decision taken after the adapter stage (scanner_epi2me.py:57-82 / scanner_dual.py:57-110).
