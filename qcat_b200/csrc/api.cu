@@ -511,9 +511,10 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
     // (window lengths are validated chunk by chunk, right before a chunk is copied: off the critical path of a large call)
     QCB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = p->stream, s_in = p->copy_in, s_out = p->copy_out;
-    // Pipeline granularity: at least 64 Ki reads per chunk (small kernels lose time in their last wave of tiles), larger
-    // for big calls as long as ~8 chunks remain to overlap the copies with the kernels, never above the device chunk.
-    static const long long chunk_div = getenv("QCB_HOST_CHUNK_DIV") ? std::max(1, atoi(getenv("QCB_HOST_CHUNK_DIV"))) : 8;
+    // Pipeline granularity: regular chunks of a quarter of the call, at least 64 Ki reads (small launches lose time in
+    // their last wave of tiles and in launch gaps), never above the device chunk; the first chunks are an eighth, a
+    // quarter and a half of that (see the chunk list below), so the kernels start after a short first copy.
+    static const long long chunk_div = getenv("QCB_HOST_CHUNK_DIV") ? std::max(1, atoi(getenv("QCB_HOST_CHUNK_DIV"))) : 4;
     long long chunk = std::max<long long>(p->host_chunk_reads, (n_reads / chunk_div + 31) / 32 * 32);
     chunk = std::min<long long>(chunk, p->chunk_reads);
     if ((long long)stride * chunk > (1LL << 27)) chunk = std::max<long long>(1, (1LL << 27) / stride);
@@ -527,15 +528,15 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
         if (p->auto_kit.reserve((size_t)n_batches * 4)) return 1;
     }
     // the chunks of this call: the whole input, or this device's blocks of a multi-device call
-    // The first two chunks are a quarter and a half of the regular size: the pipeline starts computing sooner.
+    // The first three chunks are an eighth, a quarter and a half of the regular size: computing starts sooner.
     std::vector<std::pair<long long, long long>> chunks;
     const long long unit = auto_mode ? batch_size : 32;
     for (long long base = shard ? shard->first : 0; base < n_reads; base += shard ? shard->period : n_reads) {
         const long long end = std::min<long long>(n_reads, base + span);
         for (long long off = base; off < end;) {
             long long size = chunk;
-            if (chunks.size() < 2 && chunk >= (1 << 16))
-                size = std::max<long long>(unit, (chunk >> (2 - chunks.size())) / unit * unit);
+            if (chunks.size() < 3 && chunk >= (1 << 16))
+                size = std::max<long long>(unit, (chunk >> (3 - chunks.size())) / unit * unit);
             size = std::min<long long>(size, end - off);
             chunks.emplace_back(off, size);
             off += size;

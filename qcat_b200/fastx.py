@@ -311,6 +311,69 @@ def _filter_barcodes(tables, results, batch_size):
             view[drop] = np.array((-1, -1, 0.0, 0, 0, 0, 1), dtype=_ffi.RESULT_DTYPE)
 
 
+class _BatchStraddler(object):
+    """Batch semantics of the CLI loop (cli.py:500-513: consecutive batches of `batch_size` reads, each with its own kit
+    vote / barcode filter) over chunks that end anywhere.  The windows of the reads behind the last complete batch are
+    kept (`tail`) and scored together with the following chunk's; a chunk is handed on once all of its reads have
+    results, so chunks leave in input order, at most one scoring call later than they arrived."""
+
+    def __init__(self, batch_size):
+        self.batch_size = int(batch_size)
+        self.open = []            # [chunk, read_len, results, reads filled so far], in input order
+        self.tail = None          # packed windows of the reads that do not have results yet
+
+    def _pending(self, packed):
+        if self.tail is None:
+            return packed
+        return tuple(np.concatenate([t, p]) for t, p in zip(self.tail, packed))
+
+    def _distribute(self, scored):
+        """Hand `scored` (results of the first reads without results, in input order) to the open chunks."""
+        finished, pos = [], 0
+        while pos < len(scored) and self.open:
+            entry = self.open[0]
+            chunk, read_len, results, filled = entry
+            take = min(len(results) - filled, len(scored) - pos)
+            results[filled:filled + take] = scored[pos:pos + take]
+            entry[3] = filled + take
+            pos += take
+            if entry[3] == len(results):
+                finished.append((chunk, read_len, results))
+                self.open.pop(0)
+            else:
+                break
+        assert pos == len(scored), "scored more reads than are waiting"
+        return finished
+
+    def add(self, chunk, packed, score):
+        self.open.append([chunk, packed[3], np.zeros(len(packed[2]), dtype=_ffi.RESULT_DTYPE), 0])
+        pending = self._pending(packed)
+        n_full = len(pending[2]) // self.batch_size * self.batch_size
+        if n_full == 0:
+            self.tail = pending
+            return []
+        scored = score(tuple(a[:n_full] for a in pending))
+        self.tail = tuple(np.ascontiguousarray(a[n_full:]) for a in pending) if n_full < len(pending[2]) else None
+        return self._distribute(scored)
+
+    def finish(self, score):
+        """The file's last, possibly short, batch."""
+        if self.tail is None or not len(self.tail[2]):
+            assert not self.open
+            return []
+        scored = score(self.tail)
+        self.tail = None
+        finished = self._distribute(scored)
+        assert not self.open
+        return finished
+
+    def release_all(self, failed):
+        if failed:
+            for entry in self.open:
+                entry[0].release()
+            self.open = []
+
+
 class _Writer(object):
     """Formats and writes one chunk's records; keeps the running counts."""
 
@@ -456,13 +519,17 @@ def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min
     packed_q = queue.Queue(maxsize=2)
     scored_q = queue.Queue(maxsize=2)
     failure = []
-    # batches only matter when there is a kit vote or a per-batch barcode filter; chunks aligned to batches carry up to
-    # one batch of bytes from chunk to chunk, so they are made larger
+    # Batches only matter when there is a kit vote or a per-batch barcode filter.  The reader then still cuts the file
+    # wherever records end: the windows (332 B per read) of the reads behind a chunk's last complete batch wait for the
+    # next chunk and are scored with it (`_BatchStraddler`), so no file bytes are moved to keep batches aligned.  Only
+    # --detect-middle, which needs the bytes of every read of a batch at scoring time, asks the reader for aligned chunks
+    # (those carry up to one batch of bytes from chunk to chunk, so they are made larger).
     batched = not nobatch and ((plan.tables.mode != 2 and len(set(l.kit for l in scanner.layouts)) > 1) or
                                getattr(scanner, "enable_filter_barcodes", False))
-    multiple_of = batch_size if batched else 1
+    straddle = batched and not getattr(scanner, "scan_middle_adapter", False)
+    multiple_of = batch_size if (batched and not straddle) else 1
     if chunk_bytes is None:
-        chunk_bytes = (256 << 20) if batched else (64 << 20)
+        chunk_bytes = (256 << 20) if multiple_of > 1 else (64 << 20)
 
     def produce():
         reader = None
@@ -505,26 +572,43 @@ def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min
     producer.start()
     consumer.start()
     drained = False
+    straddler = _BatchStraddler(batch_size) if straddle else None
+
+    def emit(chunk, read_len, results):
+        if keep_records:
+            all_records.append(results)
+        scored_q.put((chunk, read_len, results))
+
     try:
         while True:
             item = packed_q.get()
             if item is _STOP:
                 drained = True
+                if straddler is not None and not failure:
+                    try:
+                        for done_chunk in straddler.finish(lambda packed: _score_chunk(scanner, plan, packed, batch_size, nobatch)):
+                            emit(*done_chunk)
+                    except BaseException as exc:               # noqa: BLE001
+                        failure.append(exc)
                 break
             chunk, packed = item
             if failure:
                 chunk.release()
                 continue
             try:
-                results = _score_chunk(scanner, plan, packed, batch_size, nobatch, chunk, qcat_config)
+                if straddler is not None:
+                    finished = straddler.add(chunk, packed, lambda packed: _score_chunk(scanner, plan, packed, batch_size, nobatch))
+                else:
+                    finished = [(chunk, packed[3], _score_chunk(scanner, plan, packed, batch_size, nobatch, chunk, qcat_config))]
             except BaseException as exc:                       # noqa: BLE001
                 failure.append(exc)
                 chunk.release()
                 continue
-            if keep_records:
-                all_records.append(results)
-            scored_q.put((chunk, packed[3], results))
+            for done_chunk in finished:
+                emit(*done_chunk)
     finally:
+        if straddler is not None:
+            straddler.release_all(failed=bool(failure) or not drained)
         if not drained:                                        # interrupted while waiting: let the reader thread finish
             failure.append(sys.exc_info()[1] or RuntimeError("demux_file aborted"))
             while True:
