@@ -330,18 +330,17 @@ class _BatchStraddler(object):
     def _distribute(self, scored):
         """Hand `scored` (results of the first reads without results, in input order) to the open chunks."""
         finished, pos = [], 0
-        while pos < len(scored) and self.open:
+        while self.open:
             entry = self.open[0]
             chunk, read_len, results, filled = entry
             take = min(len(results) - filled, len(scored) - pos)
             results[filled:filled + take] = scored[pos:pos + take]
             entry[3] = filled + take
             pos += take
-            if entry[3] == len(results):
-                finished.append((chunk, read_len, results))
-                self.open.pop(0)
-            else:
+            if entry[3] < len(results):
                 break
+            finished.append((chunk, read_len, results))         # (a chunk without reads is complete at once)
+            self.open.pop(0)
         assert pos == len(scored), "scored more reads than are waiting"
         return finished
 
@@ -351,7 +350,7 @@ class _BatchStraddler(object):
         n_full = len(pending[2]) // self.batch_size * self.batch_size
         if n_full == 0:
             self.tail = pending
-            return []
+            return self._distribute(np.zeros(0, dtype=_ffi.RESULT_DTYPE))
         scored = score(tuple(a[:n_full] for a in pending))
         self.tail = tuple(np.ascontiguousarray(a[n_full:]) for a in pending) if n_full < len(pending[2]) else None
         return self._distribute(scored)
@@ -359,8 +358,9 @@ class _BatchStraddler(object):
     def finish(self, score):
         """The file's last, possibly short, batch."""
         if self.tail is None or not len(self.tail[2]):
+            finished = self._distribute(np.zeros(0, dtype=_ffi.RESULT_DTYPE))
             assert not self.open
-            return []
+            return finished
         scored = score(self.tail)
         self.tail = None
         finished = self._distribute(scored)

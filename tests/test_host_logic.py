@@ -289,3 +289,55 @@ def test_vectorised_filter_barcodes_equals_reference_rule():
     for g, w in zip(got, want):
         assert (g["barcode"] < 0) == (w["barcode"] is None)
         assert (int(g["trim5p"]), int(g["trim3p"]), int(g["exit_status"])) == (w["trim5p"], w["trim3p"], w["exit_status"])
+
+
+def test_batch_straddler_equals_plain_batching():
+    """fastx._BatchStraddler: chunks that end anywhere still give every read the result its CLI batch (consecutive
+    groups of `batch_size` reads, cli.py:500-513) would give it, chunks leave complete and in input order."""
+    from qcat_b200 import _ffi, fastx
+
+    class FakeChunk(object):
+        def __init__(self, ident):
+            self.ident, self.released = ident, False
+
+        def release(self):
+            self.released = True
+
+    rng = np.random.default_rng(12)
+    for trial in range(30):
+        batch_size = int(rng.integers(1, 40))
+        sizes = [int(v) for v in rng.integers(0, 3 * batch_size, size=int(rng.integers(1, 25)))]
+        total = sum(sizes)
+        read_ids = np.arange(total, dtype=np.int64)
+        calls = []
+
+        def score(packed):
+            # a "score" that depends on the composition of the batch a read is in: (first read of its batch, batch size)
+            ids = packed[3]
+            calls.append(len(ids))
+            out = np.zeros(len(ids), dtype=_ffi.RESULT_DTYPE)
+            for lo in range(0, len(ids), batch_size):
+                part = ids[lo:lo + batch_size]
+                out["trim5p"][lo:lo + len(part)] = part[0]
+                out["trim3p"][lo:lo + len(part)] = len(part)
+                out["adapter_end"][lo:lo + len(part)] = part - part[0]
+            return out
+
+        straddler = fastx._BatchStraddler(batch_size)
+        done, pos = [], 0
+        for ident, n in enumerate(sizes):
+            ids = read_ids[pos:pos + n]
+            pos += n
+            packed = (np.zeros((n, 16), np.uint8), np.zeros((n, 16), np.uint8), np.zeros(n, np.int32), ids)
+            done += straddler.add(FakeChunk(ident), packed, score)
+        done += straddler.finish(score)
+        straddler.release_all(failed=False)
+        assert [c.ident for c, _, _ in done] == list(range(len(sizes)))
+        assert all(n % batch_size == 0 for n in calls[:-1]) or not calls
+        got = np.concatenate([r for _, _, r in done]) if done else np.zeros(0, dtype=_ffi.RESULT_DTYPE)
+        assert len(got) == total
+        np.testing.assert_array_equal(got["trim5p"], read_ids // batch_size * batch_size)
+        np.testing.assert_array_equal(got["adapter_end"], read_ids % batch_size)
+        np.testing.assert_array_equal(got["trim3p"], np.minimum(batch_size, total - read_ids // batch_size * batch_size))
+        for (chunk, read_len, results), n in zip(done, sizes):
+            assert len(results) == n and len(read_len) == n and not chunk.released
