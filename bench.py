@@ -408,6 +408,32 @@ class Workload(object):
         res = {"value": self.world * self.n * steps / dt, "unit": "reads/s",
                "h2d_bytes_per_step": int(self.n * (2 * self.stride + 4 + 8)), "d2h_bytes_per_step": int(self.n * 32),
                "api": "qcb_detect_auto" if self.spec.get("auto") else "qcb_detect", "buffers": "pinned host"}
+        # the same call on 4-bit windows (what the native ingest hands over: two base classes per byte, packed on the
+        # host outside the timed region exactly like the ASCII windows are cut outside it): half the H2D bytes
+        if self.plan.base_classes() is not None and not self.args.force_generic:
+            p5 = torch.from_numpy(self.plan.pack4(self.batch["win5"], self.batch["wlen"])).pin_memory()
+            p3 = torch.from_numpy(self.plan.pack4(self.batch["tail3"], self.batch["wlen"])).pin_memory()
+            out4 = torch.zeros(self.n * 32, dtype=torch.uint8).pin_memory()
+            view4 = out4.numpy().view(_ffi.RESULT_DTYPE)
+
+            def run4():
+                if self.spec.get("auto"):
+                    self.plan.detect_auto4(p5.numpy(), p3.numpy(), hv["wlen"], hv["read_len"], self.kit_of_layout, 4000, out=view4)
+                else:
+                    self.plan.detect4(p5.numpy(), p3.numpy(), hv["wlen"], hv["read_len"], out=view4)
+            for _ in range(2):
+                run4()
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                run4()
+            torch.cuda.synchronize()
+            dt4 = self.max_over_ranks(time.perf_counter() - t0)
+            assert np.array_equal(view4.view(np.uint8), out_view.view(np.uint8)), "4-bit windows gave different records"
+            res["four_bit_windows"] = {"value": self.world * self.n * steps / dt4, "unit": "reads/s",
+                                       "h2d_bytes_per_step": int(self.n * (2 * p5.shape[1] + 4 + 8)),
+                                       "api": "qcb_detect_auto4" if self.spec.get("auto") else "qcb_detect4",
+                                       "records": "byte-identical to the ASCII call's"}
         return res, out_view
 
     def parity_head(self, records, count=2000):

@@ -155,6 +155,31 @@ int qcb_detect_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t *d_ta
                       const int32_t *d_wlen, const int64_t *d_read_len, int64_t n_reads,
                       const int32_t *subset /* host */, int32_t n_subset, qcb_result *d_out, void *stream);
 
+/* ---- 4-bit windows ------------------------------------------------------------------------------------------------------
+ * Everything the path does with a base goes through the two matrix mappers and the complement table (config.py:236-253,
+ * utils.py:26-27), so bytes that agree on (adapter code, barcode code, codes of the complement) are interchangeable.
+ * qcb_plan_base_classes writes that equivalence as a byte -> class table (classes 0 .. n-1; returns n, or 0 when the
+ * plan's tables need more than 16 classes) and the packed entry points take windows with two classes per byte (even
+ * position in the low nibble; slots of stride4 >= W / 2 bytes, a multiple of 8): half the host -> device traffic of the
+ * ASCII form, same records.  qcb_pack_windows4 cuts indexed records straight into that form, qcb_pack_ascii4 converts
+ * ASCII windows (host side, no GPU involved). */
+int qcb_plan_base_classes(qcb_plan *plan, uint8_t *cls /* [256] */);
+
+int qcb_detect4(qcb_plan *plan, const uint8_t *win5p, const uint8_t *tail3p, int32_t stride4,
+                const int32_t *wlen, const int64_t *read_len, int64_t n_reads,
+                const int32_t *subset, int32_t n_subset, qcb_result *out);
+
+int qcb_detect4_device(qcb_plan *plan, const uint8_t *d_win5p, const uint8_t *d_tail3p, int32_t stride4,
+                       const int32_t *d_wlen, const int64_t *d_read_len, int64_t n_reads,
+                       const int32_t *subset /* host */, int32_t n_subset, qcb_result *d_out, void *stream);
+
+int qcb_detect_auto4(qcb_plan *plan, const uint8_t *win5p, const uint8_t *tail3p, int32_t stride4,
+                     const int32_t *wlen, const int64_t *read_len, int64_t n_reads,
+                     const int32_t *kit_of_layout, int32_t batch_size, qcb_result *out, int32_t *batch_kit);
+
+int qcb_pack_ascii4(const uint8_t *windows, int32_t stride, const int32_t *wlen, int64_t n, const uint8_t *cls,
+                    uint8_t *packed, int32_t stride4, int32_t threads);
+
 /* BarcodeScanner.scan (scanner_epi2me.py:33-144 / scanner_dual.py:35-146) for n_windows already-oriented windows
  * of any length (wlen[i] <= stride): one record per window with trim5p = trim3p = 0 and exit_status 0, or the
  * empty record (layout -1, exit_status 1) where the reference returns empty_return_dict().  Host buffers. */
@@ -231,6 +256,10 @@ int qcb_fastx_index(const char *buf, int64_t len, int32_t final_chunk, qcb_fastx
 /* win5[i] = read[:W], tail3[i] = read[-W:], wlen, read_len for indexed records (the buffers qcb_detect takes). */
 int qcb_pack_windows(const char *buf, const qcb_fastx_record *recs, int64_t n, int32_t W, int32_t stride,
                      uint8_t *win5, uint8_t *tail3, int32_t *wlen, int64_t *read_len, int32_t threads);
+
+/* qcb_pack_windows in the 4-bit form (see qcb_plan_base_classes): win5p / tail3p slots of stride4 bytes. */
+int qcb_pack_windows4(const char *buf, const qcb_fastx_record *recs, int64_t n, int32_t W, int32_t stride4, const uint8_t *cls,
+                      uint8_t *win5p, uint8_t *tail3p, int32_t *wlen, int64_t *read_len, int32_t threads);
 
 /* Format records into per-bin byte strings ("@name comment\nSEQ\n+\nQUAL\n" / ">name comment\nSEQ\n"), trimmed to
  * [trim5p:trim3p] when trim != 0 and dropped when shorter than min_read_length (cli.py:521-552 with -b).  Call once

@@ -101,7 +101,8 @@ def tables_struct(tables):
 
 # Every symbol include/qcat_b200.h declares (tests check the library exports all of them).
 EXPORTS = ("qcb_device_count", "qcb_last_error", "qcb_version", "qcb_plan_create", "qcb_plan_destroy", "qcb_plan_info",
-           "qcb_plan_set_force_generic", "qcb_plan_set_profiling", "qcb_plan_stage_times", "qcb_sg_batch", "qcb_sg_stats_batch", "qcb_scan", "qcb_detect", "qcb_detect_device", "qcb_detect_auto", "qcb_detect_auto_device", "qcb_detect_multi", "qcb_detect_auto_multi", "qcb_hist_allgather", "qcb_kit_vote",
+           "qcb_plan_set_force_generic", "qcb_plan_set_profiling", "qcb_plan_stage_times", "qcb_sg_batch", "qcb_sg_stats_batch", "qcb_scan", "qcb_detect", "qcb_detect_device", "qcb_detect_auto", "qcb_detect_auto_device", "qcb_plan_base_classes", "qcb_detect4", "qcb_detect4_device",
+           "qcb_detect_auto4", "qcb_pack_ascii4", "qcb_pack_windows4", "qcb_detect_multi", "qcb_detect_auto_multi", "qcb_hist_allgather", "qcb_kit_vote",
            "qcb_kit_vote_device", "qcb_histogram_device", "qcb_microbench_cell_rate", "qcb_io_last_error", "qcb_fastx_index",
            "qcb_pack_windows", "qcb_format_records", "qcb_fastx_index_mt", "qcb_format_stream", "qcb_format_tsv",
            "qcb_write_bins", "qcb_reader_open", "qcb_reader_next", "qcb_chunk_data", "qcb_chunk_records", "qcb_chunk_release", "qcb_reader_close")
@@ -152,6 +153,18 @@ def load():
     lib.qcb_detect_auto.argtypes = [vp, vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int64, vp, ctypes.c_int32, vp, vp]
     lib.qcb_detect_auto_device.restype = ctypes.c_int
     lib.qcb_detect_auto_device.argtypes = [vp, vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int64, vp, ctypes.c_int32, vp, vp, vp]
+    lib.qcb_plan_base_classes.restype = ctypes.c_int
+    lib.qcb_plan_base_classes.argtypes = [vp, vp]
+    lib.qcb_detect4.restype = ctypes.c_int
+    lib.qcb_detect4.argtypes = lib.qcb_detect.argtypes
+    lib.qcb_detect4_device.restype = ctypes.c_int
+    lib.qcb_detect4_device.argtypes = lib.qcb_detect_device.argtypes
+    lib.qcb_detect_auto4.restype = ctypes.c_int
+    lib.qcb_detect_auto4.argtypes = lib.qcb_detect_auto.argtypes
+    lib.qcb_pack_ascii4.restype = ctypes.c_int
+    lib.qcb_pack_ascii4.argtypes = [vp, ctypes.c_int32, vp, ctypes.c_int64, vp, vp, ctypes.c_int32, ctypes.c_int32]
+    lib.qcb_pack_windows4.restype = ctypes.c_int
+    lib.qcb_pack_windows4.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp, vp, ctypes.c_int32]
     lib.qcb_detect_multi.restype = ctypes.c_int
     lib.qcb_detect_multi.argtypes = [vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int64, vp, ctypes.c_int32, vp]
     lib.qcb_detect_auto_multi.restype = ctypes.c_int

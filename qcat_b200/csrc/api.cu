@@ -75,6 +75,10 @@ struct qcb_plan {
     // workspace, sized per chunk of reads
     DeviceBuffer wins, codes, ad_score, ad_end, sel, bc_score, subset_dev, misc, long_part, long_row;
     DeviceBuffer bc_endq;                           // simple mode: end_query per (window, barcode)
+    DeviceBuffer unp;                               // 4-bit windows unpacked to representative ASCII (generic kernels only)
+    int n_classes = 0;                              // base classes of the 4-bit window format (0: not available)
+    uint8_t h_cls[256] = {0};                       // byte -> class
+    void *cls_dev = nullptr;                        // device: fwd[16] | rev[16] | rep[16]
     DeviceBuffer auto_vote, auto_kit, auto_map;   // auto-kit flow: per-read vote, per-batch kit, layout -> kit table
     int long_ov = 0;                 // warm-up rows of k_adapter_long (0 = chunking not provably exact for these tables)
     cudaStream_t stream = nullptr;   // kernels of the host-buffer entry points
@@ -172,6 +176,33 @@ int upload_tables(qcb_plan *p, const qcb_tables *h)
     }
     for (int b = 0; b < nt; ++b) p->max_template = std::max(p->max_template, h->tmpl_off[b + 1] - h->tmpl_off[b]);
     {
+        // Base classes of the 4-bit window format: bytes with equal (adapter code, barcode code) as they stand and
+        // complemented are interchangeable on this path.  Class numbers follow the first byte value of every class.
+        std::vector<uint32_t> keys;
+        uint8_t tabs[48] = {0};
+        p->n_classes = 0;
+        bool ok = true;
+        for (int b = 0; b < 256 && ok; ++b) {
+            const uint8_t c = h->comp[b];
+            const uint32_t key = (uint32_t)h->amap[b] | ((uint32_t)h->bmap[b] << 8) | ((uint32_t)h->amap[c] << 16) | ((uint32_t)h->bmap[c] << 24);
+            size_t k = 0;
+            while (k < keys.size() && keys[k] != key) ++k;
+            if (k == keys.size()) {
+                if (keys.size() == 16 || h->amap[b] > 15 || h->bmap[b] > 15 || h->amap[c] > 15 || h->bmap[c] > 15) { ok = false; break; }
+                keys.push_back(key);
+                tabs[k] = (uint8_t)(h->amap[b] | (h->bmap[b] << 4));
+                tabs[16 + k] = (uint8_t)(h->amap[c] | (h->bmap[c] << 4));
+                tabs[32 + k] = (uint8_t)b;
+            }
+            p->h_cls[b] = (uint8_t)k;
+        }
+        if (ok) {
+            p->n_classes = (int)keys.size();
+            QCB_CUDA(cudaMalloc(&p->cls_dev, sizeof tabs));
+            QCB_CUDA(cudaMemcpy(p->cls_dev, tabs, sizeof tabs, cudaMemcpyHostToDevice));
+        }
+    }
+    {
         // k_adapter_long's warm-up length: m (1 + (smax - smin) / gmin) + 1 rows for the longest adapter
         int smax = INT32_MIN, smin = INT32_MAX, max_alen = 0;
         for (int i = 0; i < h->amat_size * h->amat_size; ++i) { smax = std::max(smax, h->amat[i]); smin = std::min(smin, h->amat[i]); }
@@ -243,9 +274,28 @@ struct AutoKit {
 // d_tail3 == nullptr selects window mode: d_win5 holds n already-oriented windows (BarcodeScanner.scan).
 int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int stride, const int32_t *d_wlen,
               const int64_t *d_read_len, long long n, const int32_t *d_subset, const int32_t *h_subset, int n_subset,
-              qcb_result *d_out, int32_t *d_vote, cudaStream_t st, const AutoKit *autokit = nullptr)
+              qcb_result *d_out, int32_t *d_vote, cudaStream_t st, const AutoKit *autokit = nullptr, bool packed4 = false)
 {
     const bool window_mode = d_tail3 == nullptr;
+    if (packed4) {
+        // `stride` counts the bytes of a 4-bit slot; the kernels see windows of 2 * stride bases.  The packed kernels
+        // take the classes straight into their code bytes; a generic stage needs ASCII, so representative bytes are
+        // written out first (one byte per class: same codes, same complement codes, hence the same records).
+        const int cstride = 2 * stride;
+        const bool direct = !p->force_generic && !window_mode && p->t.mode != QCB_MODE_SIMPLE && p->fast.adapter_ok &&
+                            p->fast.barcode_ok && cstride <= kFastMaxStride && (cstride % 16) == 0 && n_subset <= 64;
+        if (!direct) {
+            if (window_mode) return fail("4-bit windows are not supported by qcb_scan");
+            if (p->unp.reserve((size_t)2 * n * cstride)) return 1;
+            uint8_t *u5 = (uint8_t *)p->unp.ptr, *u3 = u5 + (size_t)n * cstride;
+            const uint8_t *rep = (const uint8_t *)p->cls_dev + 32;
+            k_unpack4<<<grid_for(n * cstride, 256), 256, 0, st>>>(d_win5, stride, d_wlen, n, rep, u5);
+            k_unpack4<<<grid_for(n * cstride, 256), 256, 0, st>>>(d_tail3, stride, d_wlen, n, rep, u3);
+            p->launches += 2;
+            return run_chunk(p, u5, u3, cstride, d_wlen, d_read_len, n, d_subset, h_subset, n_subset, d_out, d_vote, st, autokit, false);
+        }
+        stride = cstride;
+    }
     const int wshift = window_mode ? 0 : 1;
     const long long nw = window_mode ? n : 2 * n;
     const DevTables &t = p->t;
@@ -297,8 +347,12 @@ int run_chunk(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int st
         StageTimer timer(p, 0, st);
         if (fast_ok) {
             if (p->codes.reserve((size_t)nw * stride)) return 1;
-            k_map_codes<<<grid_for(nw * (stride / 16), 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, t.amap, t.bmap,
-                                                                        (uint8_t *)p->codes.ptr);
+            if (packed4)
+                k_map_codes4<<<grid_for(nw * (stride / 16), 256), 256, 0, st>>>(d_win5, d_tail3, stride / 2, d_wlen, n,
+                                                                             (const uint8_t *)p->cls_dev, (uint8_t *)p->codes.ptr);
+            else
+                k_map_codes<<<grid_for(nw * (stride / 16), 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, t.amap, t.bmap,
+                                                                            (uint8_t *)p->codes.ptr);
         }
         if (!packed_only) {                  // a generic stage will run: it reads the oriented ASCII windows
             k_orient<<<grid_for(nw * stride, 256), 256, 0, st>>>(d_win5, d_tail3, stride, d_wlen, n, t.comp, (uint8_t *)p->wins.ptr);
@@ -434,11 +488,15 @@ int auto_prepare(qcb_plan *p, const AutoCall *ac, int64_t n_reads, int &n_kits, 
 
 int detect_device_impl(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail3, int32_t stride, const int32_t *d_wlen,
                        const int64_t *d_read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset,
-                       qcb_result *d_out, int32_t *d_vote, cudaStream_t st, const AutoCall *ac = nullptr)
+                       qcb_result *d_out, int32_t *d_vote, cudaStream_t st, const AutoCall *ac = nullptr, bool packed4 = false)
 {
     if (!p) return fail("plan is NULL");
     if (n_reads < 0) return fail("n_reads is negative");
-    if (d_tail3 && stride < p->t.W) return fail("stride %d smaller than max_align_length %d", stride, p->t.W);
+    if (packed4 && (p->n_classes <= 0 || (stride % 8) != 0))
+        return fail(p->n_classes <= 0 ? "this plan's tables need more than 16 base classes: no 4-bit window format"
+                                      : "4-bit window slots must be a multiple of 8 bytes");
+    if (d_tail3 && (packed4 ? 2 * stride : stride) < p->t.W)
+        return fail("window slots of %d bases are smaller than max_align_length %d", packed4 ? 2 * stride : stride, p->t.W);
     QCB_CUDA(cudaSetDevice(p->device));
     if (n_reads == 0) return 0;
     std::vector<int32_t> h_subset;
@@ -461,7 +519,7 @@ int detect_device_impl(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail
             for (long long off = 0; off < n_reads && !rc; off += dev_chunk) {
                 long long n = std::min<long long>(dev_chunk, n_reads - off);
                 rc = run_chunk(p, d_win5 + off * stride, d_tail3 + off * stride, stride, d_wlen + off, nullptr, n, d_subset,
-                               h_subset.data(), (int)h_subset.size(), nullptr, vote + off, st);
+                               h_subset.data(), (int)h_subset.size(), nullptr, vote + off, st, nullptr, packed4);
             }
             if (rc) return 1;
             k_batch_kit<<<grid_for(n_reads, ac->batch_size), 256, 0, st>>>(vote, n_reads, ac->batch_size, ak.d_kit_of_layout, ak.n_kits,
@@ -475,7 +533,7 @@ int detect_device_impl(qcb_plan *p, const uint8_t *d_win5, const uint8_t *d_tail
         ak.read_offset = off;
         if (run_chunk(p, d_win5 + off * stride, d_tail3 ? d_tail3 + off * stride : nullptr, stride, d_wlen + off,
                       d_read_len ? d_read_len + off : nullptr, n, d_subset, h_subset.data(), (int)h_subset.size(),
-                      d_out ? d_out + off : nullptr, d_vote ? d_vote + off : nullptr, st, ac ? &ak : nullptr))
+                      d_out ? d_out + off : nullptr, d_vote ? d_vote + off : nullptr, st, ac ? &ak : nullptr, packed4))
             return 1;
     }
     return 0;
@@ -501,7 +559,7 @@ int validate_wlen(const qcb_plan *p, const int32_t *wlen, int64_t n_reads, int32
 int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int32_t stride, const int32_t *wlen,
                      const int64_t *read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset,
                      qcb_result *out, int32_t *vote, const int32_t *kit_of_layout = nullptr, int32_t batch_size = 0,
-                     int32_t *batch_kit_out = nullptr, const Shard *shard = nullptr)
+                     int32_t *batch_kit_out = nullptr, const Shard *shard = nullptr, bool packed4 = false)
 {
     if (!p) return fail("plan is NULL");
     if (n_reads < 0) return fail("n_reads is negative");
@@ -568,7 +626,7 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
         }
         uint8_t *d = (uint8_t *)p->in_stage2[b].ptr;
         void *d_res = p->out_stage2[b].ptr;
-        if (validate_wlen(p, wlen + off, n, stride, window_mode, off)) { rc = 1; break; }
+        if (validate_wlen(p, wlen + off, n, packed4 ? 2 * stride : stride, window_mode, off)) { rc = 1; break; }
         LOOP_CUDA(cudaMemcpyAsync(d, win5 + off * stride, b_win, cudaMemcpyHostToDevice, s_in));
         if (!window_mode) { LOOP_CUDA(cudaMemcpyAsync(d + o_tail, tail3 + off * stride, b_win, cudaMemcpyHostToDevice, s_in)); }
         LOOP_CUDA(cudaMemcpyAsync(d + o_len, wlen + off, b_len, cudaMemcpyHostToDevice, s_in));
@@ -578,7 +636,7 @@ int detect_host_impl(qcb_plan *p, const uint8_t *win5, const uint8_t *tail3, int
         AutoCall ac{kit_of_layout, batch_size, auto_mode ? (int32_t *)p->auto_kit.ptr + off / batch_size : nullptr};
         rc = detect_device_impl(p, d, window_mode ? nullptr : d + o_tail, stride, (const int32_t *)(d + o_len),
                                 (const int64_t *)(d + o_rl), n, subset, n_subset, vote ? nullptr : (qcb_result *)d_res,
-                                vote ? (int32_t *)d_res : nullptr, st, auto_mode ? &ac : nullptr);
+                                vote ? (int32_t *)d_res : nullptr, st, auto_mode ? &ac : nullptr, packed4);
         if (rc) break;
         LOOP_CUDA(cudaEventRecord(p->ev_compute[b], st));
         LOOP_CUDA(cudaStreamWaitEvent(s_out, p->ev_compute[b], 0));
@@ -644,7 +702,8 @@ void qcb_plan_destroy(qcb_plan *p)
     fast_plan_free(p->fast);
     p->wins.release(); p->codes.release(); p->ad_score.release(); p->ad_end.release(); p->sel.release(); p->bc_score.release();
     p->subset_dev.release(); p->misc.release(); p->long_part.release(); p->long_row.release();
-    p->auto_vote.release(); p->auto_kit.release(); p->auto_map.release(); p->bc_endq.release();
+    p->auto_vote.release(); p->auto_kit.release(); p->auto_map.release(); p->bc_endq.release(); p->unp.release();
+    if (p->cls_dev) cudaFree(p->cls_dev);
     if (p->slab) cudaFree(p->slab);
     for (int i = 0; i < 2; ++i) {
         p->in_stage2[i].release(); p->out_stage2[i].release();
@@ -813,6 +872,40 @@ int qcb_detect_auto_device(qcb_plan *plan, const uint8_t *d_win5, const uint8_t 
     AutoCall ac{kit_of_layout, batch_size, d_batch_kit};
     return detect_device_impl(plan, d_win5, d_tail3, stride, d_wlen, d_read_len, n_reads, nullptr, 0, d_out, nullptr,
                               (cudaStream_t)stream, &ac);
+}
+
+int qcb_plan_base_classes(qcb_plan *plan, uint8_t *cls)
+{
+    if (!plan || !cls) { fail("NULL argument"); return 0; }
+    if (plan->n_classes > 0) memcpy(cls, plan->h_cls, 256);
+    return plan->n_classes;
+}
+
+int qcb_detect4(qcb_plan *plan, const uint8_t *win5p, const uint8_t *tail3p, int32_t stride4, const int32_t *wlen,
+                const int64_t *read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset, qcb_result *out)
+{
+    if (!tail3p) return fail("NULL input/output buffer");
+    return detect_host_impl(plan, win5p, tail3p, stride4, wlen, read_len, n_reads, subset, n_subset, out, nullptr, nullptr, 0, nullptr,
+                            nullptr, true);
+}
+
+int qcb_detect4_device(qcb_plan *plan, const uint8_t *d_win5p, const uint8_t *d_tail3p, int32_t stride4, const int32_t *d_wlen,
+                       const int64_t *d_read_len, int64_t n_reads, const int32_t *subset, int32_t n_subset,
+                       qcb_result *d_out, void *stream)
+{
+    if (!d_win5p || !d_tail3p || !d_wlen || !d_read_len || !d_out) return n_reads == 0 ? 0 : fail("NULL device buffer");
+    return detect_device_impl(plan, d_win5p, d_tail3p, stride4, d_wlen, d_read_len, n_reads, subset, n_subset, d_out, nullptr,
+                              (cudaStream_t)stream, nullptr, true);
+}
+
+int qcb_detect_auto4(qcb_plan *plan, const uint8_t *win5p, const uint8_t *tail3p, int32_t stride4, const int32_t *wlen,
+                     const int64_t *read_len, int64_t n_reads, const int32_t *kit_of_layout, int32_t batch_size,
+                     qcb_result *out, int32_t *batch_kit)
+{
+    if (!kit_of_layout) return fail("kit_of_layout is NULL");
+    if (!tail3p) return fail("NULL input/output buffer");
+    return detect_host_impl(plan, win5p, tail3p, stride4, wlen, read_len, n_reads, nullptr, 0, out, nullptr, kit_of_layout, batch_size,
+                            batch_kit, nullptr, true);
 }
 
 // One host thread per plan; plan d takes the blocks d, d + D, d + 2 D, ... of `block` reads (round-robin at block

@@ -371,6 +371,54 @@ int qcb_fastx_index_mt(const char *buf, int64_t len, int32_t final_chunk, qcb_fa
     return index_buffer(buf, len, final_chunk, recs, max_records, n_records, consumed, is_fastq, threads);
 }
 
+// Two bases per byte (even position in the low nibble) through a byte -> class table (qcb_plan_base_classes).
+static inline void pack_classes(const uint8_t *src, int k, const uint8_t *cls, uint8_t *dst, int stride4)
+{
+    memset(dst, 0, (size_t)stride4);
+    int i = 0;
+    for (; i + 1 < k; i += 2) dst[i >> 1] = (uint8_t)(cls[src[i]] | (cls[src[i + 1]] << 4));
+    if (i < k) dst[i >> 1] = cls[src[i]];
+}
+
+int qcb_pack_ascii4(const uint8_t *windows, int32_t stride, const int32_t *wlen, int64_t n, const uint8_t *cls,
+                    uint8_t *packed, int32_t stride4, int32_t threads)
+{
+    if (!windows || !wlen || !cls || !packed) return n == 0 ? 0 : io_fail("NULL argument");
+    if (stride <= 0 || stride4 * 2 < stride) return io_fail("need stride4 >= stride / 2");
+    parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i)
+            pack_classes(windows + (size_t)i * stride, std::min<int>(std::max<int>(wlen[i], 0), stride), cls,
+                         packed + (size_t)i * stride4, stride4);
+    });
+    return 0;
+}
+
+int qcb_pack_windows4(const char *buf, const qcb_fastx_record *recs, int64_t n, int32_t W, int32_t stride4, const uint8_t *cls,
+                      uint8_t *win5p, uint8_t *tail3p, int32_t *wlen, int64_t *read_len, int32_t threads)
+{
+    if (!buf || !recs || !cls || !win5p || !tail3p || !wlen || !read_len) return n == 0 ? 0 : io_fail("NULL argument");
+    if (W <= 0 || W > 4096 || stride4 * 2 < W) return io_fail("need 0 < W <= 2 * stride4 (W <= 4096)");
+    parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
+        std::vector<uint8_t> tmp((size_t)2 * W);
+        for (int64_t i = lo; i < hi; ++i) {
+            const qcb_fastx_record &r = recs[i];
+            const char *s = buf + r.seq_off, *e = s + r.seq_span;
+            const int k = (int)std::min<int64_t>(r.seq_len, W);
+            const uint8_t *h = (const uint8_t *)s, *t = (const uint8_t *)(e - k);
+            if (r.seq_span != r.seq_len) {                         // wrapped record: gather the bases line by line first
+                copy_bases(tmp.data(), s, e, 0, k, r.qual_off < 0);
+                copy_bases(tmp.data() + W, s, e, r.seq_len - k, r.seq_len, r.qual_off < 0);
+                h = tmp.data(); t = tmp.data() + W;
+            }
+            pack_classes(h, k, cls, win5p + (size_t)i * stride4, stride4);
+            pack_classes(t, k, cls, tail3p + (size_t)i * stride4, stride4);
+            wlen[i] = k;
+            read_len[i] = r.seq_len;
+        }
+    });
+    return 0;
+}
+
 int qcb_pack_windows(const char *buf, const qcb_fastx_record *recs, int64_t n, int32_t W, int32_t stride,
                      uint8_t *win5, uint8_t *tail3, int32_t *wlen, int64_t *read_len, int32_t threads)
 {

@@ -293,6 +293,54 @@ __global__ void k_map_codes(const uint8_t *__restrict__ win5, const uint8_t *__r
     ((uint4 *)codes)[id] = make_uint4(dst[0], dst[1], dst[2], dst[3]);
 }
 
+// The same from 4-bit windows (two base classes per byte, qcb_plan_base_classes): tabs = fwd[16] | rev[16], the packed
+// code byte of every class as it stands / complemented.  8 input bytes -> 16 code bytes per thread.
+__global__ void k_map_codes4(const uint8_t *__restrict__ win5p, const uint8_t *__restrict__ tail3p, int stride4,
+                             const int32_t *__restrict__ wlen, long long n_reads, const uint8_t *__restrict__ tabs,
+                             uint8_t *__restrict__ codes)
+{
+    __shared__ uint8_t s_tab[32];
+    if (threadIdx.x < 32) s_tab[threadIdx.x] = tabs[threadIdx.x];
+    __syncthreads();
+    const int stride = 2 * stride4, vecs = stride >> 4;
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_reads * 2 * vecs) return;
+    const long long w = id / vecs;
+    const int v = (int)(id % vecs);
+    const long long r = w >> 1;
+    const int len = min(max(wlen[r], 0), stride);
+    const uint8_t *tab = s_tab + ((w & 1) ? 16 : 0);
+    const uint2 in = ((const uint2 *)(((w & 1) ? tail3p : win5p) + r * stride4))[v];
+    const uint32_t src[2] = {in.x, in.y};
+    uint32_t dst[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = v * 16 + q * 4 + b;                          // base position; nibble i of the slot
+            const uint32_t cls = (src[q >> 1] >> (4 * ((q & 1) * 4 + b))) & 15u;
+            o |= (i < len ? (uint32_t)tab[cls] : 0u) << (8 * b);
+        }
+        dst[q] = o;
+    }
+    ((uint4 *)codes)[id] = make_uint4(dst[0], dst[1], dst[2], dst[3]);
+}
+
+// 4-bit windows -> ASCII windows of representative bytes (one byte per class), for the generic kernels.
+__global__ void k_unpack4(const uint8_t *__restrict__ packed, int stride4, const int32_t *__restrict__ wlen, long long n,
+                          const uint8_t *__restrict__ rep, uint8_t *__restrict__ ascii)
+{
+    const int stride = 2 * stride4;
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n * stride) return;
+    const long long r = id / stride;
+    const int i = (int)(id % stride);
+    const int len = min(max(wlen[r], 0), stride);
+    const uint32_t cls = (packed[r * stride4 + (i >> 1)] >> (4 * (i & 1))) & 15u;
+    ascii[id] = i < len ? rep[cls] : (uint8_t)0;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side: build the packed-kernel tables
 // ---------------------------------------------------------------------------------------------------

@@ -149,6 +149,67 @@ class DevicePlan(object):
                                              _vp(kits), int(batch_size), _vp(out), _vp(batch_kit)))
         return (out, batch_kit) if return_kits else out
 
+    # ---- 4-bit windows (two base classes per byte: half the host -> device traffic) --------------------
+
+    def base_classes(self):
+        """Byte -> class table (uint8[256]) of the 4-bit window format, or None when the plan's tables need more than
+        16 classes (qcb_plan_base_classes)."""
+        if not hasattr(self, "_classes"):
+            cls = np.zeros(256, dtype=np.uint8)
+            n = int(self._lib.qcb_plan_base_classes(self._handle, _vp(cls)))
+            self._classes = cls if n > 0 else None
+        return self._classes
+
+    def pack4(self, windows, wlen, threads=0):
+        """ASCII windows [n][stride] -> 4-bit windows [n][stride / 2] (qcb_pack_ascii4, host side)."""
+        cls = self.base_classes()
+        if cls is None:
+            raise _ffi.QcbError("this plan has no 4-bit window format")
+        windows = np.ascontiguousarray(windows, dtype=np.uint8)
+        wlen = np.ascontiguousarray(wlen, dtype=np.int32)
+        n, stride = windows.shape
+        stride4 = (stride // 2 + 7) // 8 * 8
+        out = np.zeros((n, stride4), dtype=np.uint8)
+        rc = self._lib.qcb_pack_ascii4(_vp(windows), stride, _vp(wlen), n, _vp(cls), _vp(out), stride4, int(threads or os.cpu_count() or 1))
+        if rc:
+            raise _ffi.QcbError("qcb_pack_ascii4 failed")
+        return out
+
+    def detect4(self, win5p, tail3p, wlen, read_len, subset=None, out=None):
+        """qcb_detect4: detect() on 4-bit windows (pack4 / fastx.pack_windows(..., classes=...))."""
+        win5p = np.ascontiguousarray(win5p, dtype=np.uint8)
+        tail3p = np.ascontiguousarray(tail3p, dtype=np.uint8)
+        wlen = np.ascontiguousarray(wlen, dtype=np.int32)
+        read_len = np.ascontiguousarray(read_len, dtype=np.int64)
+        n = int(wlen.shape[0])
+        if out is None:
+            out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+        sub, nsub = self._subset(subset)
+        _ffi.check(self._lib.qcb_detect4(self._handle, _vp(win5p), _vp(tail3p), int(win5p.shape[1]), _vp(wlen), _vp(read_len), n,
+                                         _vp(sub) if sub is not None else None, nsub, _vp(out)))
+        return out
+
+    def detect_auto4(self, win5p, tail3p, wlen, read_len, kit_of_layout, batch_size, out=None, return_kits=False):
+        win5p = np.ascontiguousarray(win5p, dtype=np.uint8)
+        tail3p = np.ascontiguousarray(tail3p, dtype=np.uint8)
+        wlen = np.ascontiguousarray(wlen, dtype=np.int32)
+        read_len = np.ascontiguousarray(read_len, dtype=np.int64)
+        kits = np.ascontiguousarray(kit_of_layout, dtype=np.int32)
+        n = int(wlen.shape[0])
+        if out is None:
+            out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+        batch_kit = np.zeros(max(1, (n + int(batch_size) - 1) // max(int(batch_size), 1)), dtype=np.int32)
+        _ffi.check(self._lib.qcb_detect_auto4(self._handle, _vp(win5p), _vp(tail3p), int(win5p.shape[1]), _vp(wlen), _vp(read_len),
+                                              n, _vp(kits), int(batch_size), _vp(out), _vp(batch_kit)))
+        return (out, batch_kit) if return_kits else out
+
+    def detect4_device(self, d_win5p, d_tail3p, stride4, d_wlen, d_read_len, n_reads, d_out, subset=None, stream=0):
+        sub, nsub = self._subset(subset)
+        _ffi.check(self._lib.qcb_detect4_device(self._handle, ctypes.c_void_p(d_win5p), ctypes.c_void_p(d_tail3p), int(stride4),
+                                                ctypes.c_void_p(d_wlen), ctypes.c_void_p(d_read_len), int(n_reads),
+                                                _vp(sub) if sub is not None else None, nsub,
+                                                ctypes.c_void_p(d_out), ctypes.c_void_p(stream)))
+
     def detect_reads(self, read_sequences, subset=None):
         win5, tail3, wlen, read_len, _ = pack_windows(read_sequences, self.tables.max_align_length)
         return self.detect(win5, tail3, wlen, read_len, subset)

@@ -60,12 +60,25 @@ def index_buffer(buf, final_chunk=True, max_records=None, threads=1):
         capacity *= 4
 
 
-def pack_windows(buf, recs, max_align_length=150, threads=None):
-    """(win5, tail3, wlen, read_len) of indexed records -- the buffers DevicePlan.detect takes."""
+def pack_windows(buf, recs, max_align_length=150, threads=None, classes=None):
+    """(win5, tail3, wlen, read_len) of indexed records -- the buffers DevicePlan.detect takes; with `classes` (a plan's
+    base_classes() table) the windows come in the 4-bit form DevicePlan.detect4 takes (two bases per byte)."""
     lib = _ffi.load()
     arr = buf if isinstance(buf, np.ndarray) else np.frombuffer(buf, dtype=np.uint8)
     n = len(recs)
     W = int(max_align_length)
+    if classes is not None:
+        stride4 = max(8, ((W + 1) // 2 + 7) // 8 * 8)
+        win5p = np.empty((n, stride4), dtype=np.uint8)
+        tail3p = np.empty((n, stride4), dtype=np.uint8)
+        wlen = np.empty(n, dtype=np.int32)
+        read_len = np.empty(n, dtype=np.int64)
+        recs = np.ascontiguousarray(recs)
+        cls = np.ascontiguousarray(classes, dtype=np.uint8)
+        if n:
+            _check_io(lib.qcb_pack_windows4(_vp(arr), _vp(recs), n, W, stride4, _vp(cls), _vp(win5p), _vp(tail3p), _vp(wlen),
+                                            _vp(read_len), _threads(threads)))
+        return win5p, tail3p, wlen, read_len
     stride = max(16, (W + 15) // 16 * 16)
     win5 = np.empty((n, stride), dtype=np.uint8)
     tail3 = np.empty((n, stride), dtype=np.uint8)
@@ -248,22 +261,25 @@ def _middle_scan_chunk(scanner, chunk, results, qcat_config):
                 results[i] = (-1, -1, 0.0, 0, results["trim5p"][i], results["trim3p"][i], 997)
 
 
-def _score_chunk(scanner, plan, packed, batch_size, nobatch, chunk=None, qcat_config=None):
-    """qcb_result records of one chunk, batch semantics of the CLI loop (cli.py:500-513)."""
+def _score_chunk(scanner, plan, packed, batch_size, nobatch, chunk=None, qcat_config=None, four_bit=False):
+    """qcb_result records of one chunk, batch semantics of the CLI loop (cli.py:500-513).  four_bit: the windows are in
+    the plan's 4-bit form (pack_windows(..., classes=plan.base_classes()))."""
     win5, tail3, wlen, read_len = packed
     tables = plan.tables
     n = len(wlen)
     results = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
     names = [layout.kit for layout in scanner.layouts]
     kit_names = list(dict.fromkeys(names))
+    detect = plan.detect4 if four_bit else plan.detect
     if tables.mode == 2:
-        plan.detect(win5, tail3, wlen, read_len, out=results)   # simple mode: no layouts, no vote (scanner_simple.py)
+        detect(win5, tail3, wlen, read_len, out=results)        # simple mode: no layouts, no vote (scanner_simple.py)
     elif nobatch or len(kit_names) == 1:
         # no vote needed (single-read mode, or every layout names the same kit): one device call per chunk
-        plan.detect(win5, tail3, wlen, read_len, scanner._subset_for(plan, scanner.layouts), out=results)
+        detect(win5, tail3, wlen, read_len, scanner._subset_for(plan, scanner.layouts), out=results)
     elif tables.kit_index()[1] is not None and hasattr(plan, "detect_auto"):
         # one pass (qcb_detect_auto): adapter stage over all layouts once, per-batch vote and kit restriction on the device
-        plan.detect_auto(win5, tail3, wlen, read_len, tables.kit_index()[1], batch_size, out=results)
+        (plan.detect_auto4 if four_bit else plan.detect_auto)(win5, tail3, wlen, read_len, tables.kit_index()[1], batch_size,
+                                                              out=results)
     else:
         vote = plan.kit_vote(win5, tail3, wlen)                 # one device call for the whole chunk
         kit_of_layout = np.array([kit_names.index(k) for k in names], dtype=np.int64)
@@ -527,6 +543,11 @@ def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min
     batched = not nobatch and ((plan.tables.mode != 2 and len(set(l.kit for l in scanner.layouts)) > 1) or
                                getattr(scanner, "enable_filter_barcodes", False))
     straddle = batched and not getattr(scanner, "scan_middle_adapter", False)
+    # windows travel to the device in the plan's 4-bit form (two base classes per byte) when it has one
+    multi_kit = plan.tables.mode != 2 and len(set(l.kit for l in scanner.layouts)) > 1
+    four_bit = (hasattr(plan, "detect4") and plan.base_classes() is not None and
+                (nobatch or not multi_kit or (plan.tables.kit_index()[1] is not None and hasattr(plan, "detect_auto4"))))
+    classes = plan.base_classes() if four_bit else None
     multiple_of = batch_size if (batched and not straddle) else 1
     if chunk_bytes is None:
         chunk_bytes = (256 << 20) if multiple_of > 1 else (64 << 20)
@@ -539,7 +560,7 @@ def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min
                 if failure:
                     chunk.release()
                     break
-                packed = pack_windows(chunk.data, chunk.recs, qcat_config.max_align_length, threads)
+                packed = pack_windows(chunk.data, chunk.recs, qcat_config.max_align_length, threads, classes=classes)
                 packed_q.put((chunk, packed))
         except BaseException as exc:                           # noqa: BLE001 -- re-raised on the caller's thread
             failure.append(exc)
@@ -586,7 +607,7 @@ def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min
                 drained = True
                 if straddler is not None and not failure:
                     try:
-                        for done_chunk in straddler.finish(lambda packed: _score_chunk(scanner, plan, packed, batch_size, nobatch)):
+                        for done_chunk in straddler.finish(lambda packed: _score_chunk(scanner, plan, packed, batch_size, nobatch, four_bit=four_bit)):
                             emit(*done_chunk)
                     except BaseException as exc:               # noqa: BLE001
                         failure.append(exc)
@@ -597,9 +618,9 @@ def demux_file(path, scanner, qcat_config=None, batch_size=4000, trim=False, min
                 continue
             try:
                 if straddler is not None:
-                    finished = straddler.add(chunk, packed, lambda packed: _score_chunk(scanner, plan, packed, batch_size, nobatch))
+                    finished = straddler.add(chunk, packed, lambda packed: _score_chunk(scanner, plan, packed, batch_size, nobatch, four_bit=four_bit))
                 else:
-                    finished = [(chunk, packed[3], _score_chunk(scanner, plan, packed, batch_size, nobatch, chunk, qcat_config))]
+                    finished = [(chunk, packed[3], _score_chunk(scanner, plan, packed, batch_size, nobatch, chunk, qcat_config, four_bit=four_bit))]
             except BaseException as exc:                       # noqa: BLE001
                 failure.append(exc)
                 chunk.release()

@@ -18,7 +18,7 @@ def lib():
 def test_header_symbols_are_exported(lib):
     from qcat_b200 import _ffi
     header = open(os.path.join(ROOT, "include", "qcat_b200.h")).read()
-    declared = sorted(set(re.findall(r"\b(qcb_[a-z_]+)\s*\(", header)))
+    declared = sorted(set(re.findall(r"\b(qcb_[a-z0-9_]+)\s*\(", header)))
     assert declared, "no declarations found in the header"
     for name in declared:
         assert hasattr(lib, name), "%s declared in include/qcat_b200.h but not exported" % name

@@ -369,3 +369,42 @@ def test_reader_streams_from_stdin_and_fifos(tmp_path):
     with open(path, "rb") as fh:
         out = subprocess.run([sys.executable, "-c", child], stdin=fh, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.split()[0] == str(len(reads)), out.stderr
+
+
+def test_four_bit_window_packers_agree_with_a_numpy_model(tmp_path):
+    """qcb_pack_windows4 (records -> 4-bit windows) and qcb_pack_ascii4 (ASCII windows -> 4-bit windows): two classes per
+    byte, even position in the low nibble, zero beyond the window; wrapped records included.  Host only."""
+    import ctypes
+    from qcat_b200 import _ffi
+    lib = _ffi.load()
+    rng = np.random.default_rng(21)
+    cls = rng.integers(0, 16, size=256).astype(np.uint8)
+    seqs = ["".join(rng.choice(list("ACGTNacgtRYX-"), size=int(n))) for n in rng.integers(0, 400, size=120)]
+    text = "".join(">r%d\n%s" % (i, "".join(s[j:j + 61] + "\n" for j in range(0, len(s), 61)) or "\n") for i, s in enumerate(seqs))
+    buf = text.encode("latin-1")
+    recs, consumed, fastq = fastx.index_buffer(buf)
+    assert len(recs) == len(seqs) and not fastq
+    W = 150
+    win5p, tail3p, wlen, read_len = fastx.pack_windows(buf, recs, W, threads=3, classes=cls)
+    assert win5p.shape == (len(seqs), 80)
+    win5, tail3, wlen_a, read_len_a = fastx.pack_windows(buf, recs, W, threads=3)
+    np.testing.assert_array_equal(wlen, wlen_a)
+    np.testing.assert_array_equal(read_len, read_len_a)
+
+    def model(windows):
+        out = np.zeros((len(windows), 80), dtype=np.uint8)
+        for i, row in enumerate(windows):
+            k = int(wlen[i])
+            c = np.zeros(160, dtype=np.uint8)
+            c[:k] = cls[row[:k]]
+            out[i] = c[0::2] | (c[1::2] << 4)
+        return out
+
+    np.testing.assert_array_equal(win5p, model(win5))
+    np.testing.assert_array_equal(tail3p, model(tail3))
+    for windows, want in ((win5, win5p), (tail3, tail3p)):
+        got = np.zeros((len(seqs), 80), dtype=np.uint8)
+        rc = lib.qcb_pack_ascii4(ctypes.c_void_p(windows.ctypes.data), 160, ctypes.c_void_p(wlen.ctypes.data), len(seqs),
+                                 ctypes.c_void_p(cls.ctypes.data), ctypes.c_void_p(got.ctypes.data), 80, 2)
+        assert rc == 0
+        np.testing.assert_array_equal(got, want)
