@@ -69,6 +69,7 @@ struct qcb_plan {
     size_t slab_bytes = 0;
     std::vector<int32_t> h_group_off, h_group, h_tmpl_off, h_adapter_off;
     std::vector<int32_t> subset_cached;   // layout subset currently held in subset_dev
+    std::vector<int32_t> bin_base_cached; // histogram bin bases currently held in misc
     int bmax0 = 0, bmax1 = 0;        // largest barcode set 0 / set 1 over all layouts
     int max_adapter = 0, max_template = 0;
     FastPlan fast;                   // packed-kernel tables (kernels_fast.cuh)
@@ -1013,10 +1014,15 @@ int qcb_histogram_device(qcb_plan *p, const qcb_result *d_results, int64_t n_rea
     if (!d_results || !layout_bin_base || !d_counts) return fail("NULL buffer");
     QCB_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (p->misc.reserve((size_t)p->t.n_layouts * 4)) return 1;
-    QCB_CUDA(cudaMemcpyAsync(p->misc.ptr, layout_bin_base, (size_t)p->t.n_layouts * 4, cudaMemcpyHostToDevice, st));
-    k_histogram<<<grid_for(n_reads, 256), 256, 0, st>>>(d_results, n_reads, (const int32_t *)p->misc.ptr,
-                                                       (unsigned long long *)d_counts, n_bins);
+    const std::vector<int32_t> base(layout_bin_base, layout_bin_base + p->t.n_layouts);
+    if (base != p->bin_base_cached || !p->misc.ptr) {                 // the bin layout stays on the device between calls
+        if (p->misc.reserve(base.size() * 4)) return 1;
+        QCB_CUDA(cudaDeviceSynchronize());                            // an earlier call may still read the old table
+        QCB_CUDA(cudaMemcpy(p->misc.ptr, base.data(), base.size() * 4, cudaMemcpyHostToDevice));
+        p->bin_base_cached = base;
+    }
+    const unsigned grid = (unsigned)std::min<long long>(grid_for(n_reads, 256), (long long)p->sm_count * 8);
+    k_histogram<<<grid, 256, 0, st>>>(d_results, n_reads, (const int32_t *)p->misc.ptr, (unsigned long long *)d_counts, n_bins);
     p->launches++;
     QCB_CUDA(cudaGetLastError());
     return 0;

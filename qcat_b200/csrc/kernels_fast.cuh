@@ -480,7 +480,10 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     int max_ctx = 0;
     for (const FastGroup &G : groups) max_ctx = std::max(max_ctx, std::max(G.u, G.d));
     const int ncol = max_ctx <= 12 ? 12 : 16;
-    fp.ctx_pair = (size_t)ng * nc * nc * ncol * 4 <= 64 * 1024;
+#ifndef QCB_CTX_PAIR_LIMIT
+#define QCB_CTX_PAIR_LIMIT (64 * 1024)
+#endif
+    fp.ctx_pair = (size_t)ng * nc * nc * ncol * 4 <= QCB_CTX_PAIR_LIMIT;
     const size_t grp_words = (size_t)(fp.ctx_pair ? nc * nc : 2 * nc) * ncol;
     std::vector<uint32_t> ctx_tab((size_t)ng * grp_words, 0u);
     for (int gi = 0; gi < ng; ++gi) {

@@ -558,15 +558,32 @@ __global__ void k_batch_kit(const int32_t *__restrict__ vote, long long n_reads,
     }
 }
 
+// Per-barcode counts (the histogram behind cli.py:386-405).  Counts are first gathered per CTA in shared memory (the
+// bins are few and hot: 97 for a 96-barcode kit), then added to the global vector with one atomic per non-empty bin.
+constexpr int kHistSharedBins = 4096;
+
 __global__ void k_histogram(const qcb_result *__restrict__ res, long long n_reads,
                             const int32_t *__restrict__ layout_bin_base, unsigned long long *__restrict__ counts, int n_bins)
 {
-    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    qcb_result o = res[r];
-    int bin = 0;
-    if (o.barcode >= 0) bin = 1 + (o.layout >= 0 ? layout_bin_base[o.layout] : 0) + o.barcode;   // layout -1: simple mode
-    if (bin >= 0 && bin < n_bins) atomicAdd(counts + bin, 1ULL);
+    __shared__ unsigned int s_cnt[kHistSharedBins];
+    const bool use_shared = n_bins <= kHistSharedBins;
+    if (use_shared) {
+        for (int i = threadIdx.x; i < n_bins; i += blockDim.x) s_cnt[i] = 0;
+        __syncthreads();
+    }
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (long long)gridDim.x * blockDim.x) {
+        const qcb_result o = res[r];
+        int bin = 0;
+        if (o.barcode >= 0) bin = 1 + (o.layout >= 0 ? layout_bin_base[o.layout] : 0) + o.barcode;   // layout -1: simple mode
+        if (bin < 0 || bin >= n_bins) continue;
+        if (use_shared) atomicAdd(&s_cnt[bin], 1u);
+        else atomicAdd(counts + bin, 1ULL);
+    }
+    if (use_shared) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_bins; i += blockDim.x)
+            if (s_cnt[i]) atomicAdd(counts + i, (unsigned long long)s_cnt[i]);
+    }
 }
 
 }  // namespace qcb
