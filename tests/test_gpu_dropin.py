@@ -206,3 +206,27 @@ def test_middle_adapter_scan_matches_reference(mode, kit):
         dropin.uninstall()
     assert [_key(r) for r in got] == [_key(r) for r in want]
     assert [_key(r) for r in got_single] == [_key(r) for r in want_single]
+
+
+def test_module_entry_point_runs_the_reference_cli(tmp_path):
+    """`python -m qcat_b200 <qcat arguments>`: the reference's own cli.main on top of the drop-in, as a subprocess (the
+    parasail stand-in and the installed reference are put on PYTHONPATH the way a real parasail + qcat would be)."""
+    import subprocess
+    refloader.load()
+    from qcat import scanner as ref_scanner
+    from qcat_b200 import dropin
+    dropin.uninstall()
+    reads = _reads(ref_scanner.factory(kit="NBD103/NBD104").layouts, 200, seed=3)
+    fastq = tmp_path / "reads.fastq"
+    with open(fastq, "w") as fh:
+        for i, r in enumerate(reads):
+            fh.write("@read%d\n%s\n+\n%s\n" % (i, r, "I" * len(r)))
+    want = _run_cli(["-f", str(fastq), "-k", "NBD103/NBD104", "--tsv"])
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([ROOT, os.path.join(ROOT, "oracle", "refshim"), refloader.REFERENCE_ROOT,
+                                         env.get("PYTHONPATH", "")])
+    for extra in ([], ["--devices", "0,0"]):
+        proc = subprocess.run([sys.executable, "-m", "qcat_b200"] + extra + ["-f", str(fastq), "-k", "NBD103/NBD104", "--tsv"],
+                              cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+        assert proc.returncode == 0, proc.stderr[-2000:]
+        assert proc.stdout == want
