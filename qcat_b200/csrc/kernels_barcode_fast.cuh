@@ -69,7 +69,7 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 __device__ __forceinline__ uint4 lds128(uint32_t addr)
 {
     uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
 
