@@ -119,13 +119,14 @@ __device__ __forceinline__ uint32_t dup16(uint32_t v) { return v * 0x00010001u; 
 // parasail end-cell rule is applied (see sg_affine in kernels_generic.cuh / qo_sg in the oracle).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kAdapterWarps = 4;
+constexpr int kAdapterPhase = 24;       // columns whose profile words are in registers at a time
 
 // CTAs per SM the register allocation of each column variant is sized for
 #ifndef QCB_AD48_BLOCKS
-#define QCB_AD48_BLOCKS 6
+#define QCB_AD48_BLOCKS 5
 #endif
 #ifndef QCB_AD64_BLOCKS
-#define QCB_AD64_BLOCKS 5
+#define QCB_AD64_BLOCKS 4
 #endif
 #ifndef QCB_AD104_BLOCKS
 #define QCB_AD104_BLOCKS 3
@@ -205,22 +206,35 @@ k_adapter_fast(const uint32_t *__restrict__ profile, int profile_words, int row_
             do {
                 const uint32_t prow = pbase + lds_u8(cp) * row_bytes;
                 cp += kTile;
-                // diagonal terms are formed from the previous row's registers one 4-column chunk ahead of the max chain,
-                // so every Wc register is updated in place (no rotation copies).
-                uint4 e = lds128(prow);
-                uint32_t t0 = border + e.x;
+                // Columns go in phases of kAdapterPhase: a phase's profile words are loaded first (volatile loads: ptxas
+                // keeps them ahead of the max chain), every diagonal term is formed one column ahead of the in-place
+                // update, and only the last column of a phase is copied (its old value starts the next phase).
+                const uint32_t border_prev = border;
                 border += gdup;
-                uint32_t left = border;
+                uint32_t left = border, t = 0, carry = border_prev;
 #pragma unroll
-                for (int c = 0; c < NC; c += 4) {
-                    uint4 en = make_uint4(0, 0, 0, 0);
-                    if (c + 4 < NC) en = lds128(prow + (c + 4) * 4);
-                    const uint32_t t1 = Wc[c] + e.y, t2 = Wc[c + 1] + e.z, t3 = Wc[c + 2] + e.w, t0n = Wc[c + 3] + en.x;
-                    left = __vimax3_u16x2(t0, Wc[c], left);     Wc[c] = left;
-                    left = __vimax3_u16x2(t1, Wc[c + 1], left); Wc[c + 1] = left;
-                    left = __vimax3_u16x2(t2, Wc[c + 2], left); Wc[c + 2] = left;
-                    left = __vimax3_u16x2(t3, Wc[c + 3], left); Wc[c + 3] = left;
-                    t0 = t0n; e = en;
+                for (int p0 = 0; p0 < NC; p0 += kAdapterPhase) {
+                    constexpr int kMaxCols = kAdapterPhase;
+                    const int cols = NC - p0 < kMaxCols ? NC - p0 : kMaxCols;
+                    uint32_t e[kMaxCols];
+#pragma unroll
+                    for (int c = 0; c < kMaxCols; c += 4) {
+                        if (c < cols) {
+                            const uint4 q = lds128(prow + (uint32_t)(p0 + c) * 4u);
+                            e[c] = q.x; e[c + 1] = q.y; e[c + 2] = q.z; e[c + 3] = q.w;
+                        }
+                    }
+                    t = e[0] + carry;
+#pragma unroll
+                    for (int c = 0; c < kMaxCols; ++c) {
+                        if (c < cols) {
+                            const uint32_t tn = c + 1 < cols ? e[c + 1] + Wc[p0 + c] : 0u;
+                            if (c == cols - 1) carry = Wc[p0 + c];
+                            left = __vimax3_u16x2(t, Wc[p0 + c], left);
+                            Wc[p0 + c] = left;
+                            t = tn;
+                        }
+                    }
                 }
                 rowc -= rowc_step;
                 best_lo = max(best_lo, (int)(left & 0xffffu) * 256 + rowc);
