@@ -176,34 +176,44 @@ k_context(FastDev f, DevTables t, const uint32_t *__restrict__ ctx_tab, const ui
         // (idle lanes, n == 0, may carry any lo: they read row 1, zeroed above)
         uint32_t pf = code_addr + (uint32_t)((n > 0 ? lo : 0) + 1) * kRowTile;
         uint32_t pg = code_addr + (uint32_t)(n > 0 ? lo + n : 1) * kRowTile;
-        for (int st = 1; st <= nmax; ++st) {
-            const uint32_t cf = lds_u8(pf), cg = lds_u8(pg);
-            if (st < n) { pf += kRowTile; pg -= kRowTile; }
-            uint32_t diag = border;
-            border += gdup;
-            uint32_t left = border - (st == n ? ((uint32_t)g << 16) : 0u);      // G's left border at its last row is -g
-            uint32_t tt[NCOL];
+        // software pipeline: the table words of step st + 1 and the base codes of step st + 2 are fetched while step st's
+        // max chain runs (the chain, not the loads, is then the critical path of a step)
+        auto fetch_words = [&](uint32_t (&e)[NCOL], uint32_t cf, uint32_t cg) {
             if (PAIR) {
                 const uint32_t pe = tab_addr + (cf * nc + cg) * (NCOL * 4);
 #pragma unroll
                 for (int c = 0; c < NCOL; c += 4) {
-                    const uint4 e = lds128(pe + c * 4);
-                    tt[c] = (c == 0 ? diag : Wc[c - 1]) + e.x;
-                    tt[c + 1] = Wc[c] + e.y;
-                    tt[c + 2] = Wc[c + 1] + e.z;
-                    tt[c + 3] = Wc[c + 2] + e.w;
+                    const uint4 v = lds128(pe + c * 4);
+                    e[c] = v.x; e[c + 1] = v.y; e[c + 2] = v.z; e[c + 3] = v.w;
                 }
             } else {
                 const uint32_t pfa = tab_addr + cf * (NCOL * 4), pga = tab_addr + (nc + cg) * (NCOL * 4);
 #pragma unroll
                 for (int c = 0; c < NCOL; c += 4) {
                     const uint4 ef = lds128(pfa + c * 4), eg = lds128(pga + c * 4);
-                    tt[c] = (c == 0 ? diag : Wc[c - 1]) + ef.x + eg.x;
-                    tt[c + 1] = Wc[c] + ef.y + eg.y;
-                    tt[c + 2] = Wc[c + 1] + ef.z + eg.z;
-                    tt[c + 3] = Wc[c + 2] + ef.w + eg.w;
+                    e[c] = ef.x + eg.x; e[c + 1] = ef.y + eg.y; e[c + 2] = ef.z + eg.z; e[c + 3] = ef.w + eg.w;
                 }
             }
+        };
+        uint32_t cf_cur = lds_u8(pf), cfn, cgn;
+        uint32_t en[NCOL];
+        fetch_words(en, cf_cur, lds_u8(pg));
+        if (1 < n) { pf += kRowTile; pg -= kRowTile; }
+        cfn = lds_u8(pf); cgn = lds_u8(pg);
+        if (2 < n) { pf += kRowTile; pg -= kRowTile; }
+#pragma unroll 2
+        for (int st = 1; st <= nmax; ++st) {
+            const uint32_t cf = cf_cur;
+            uint32_t diag = border;
+            border += gdup;
+            uint32_t left = border - (st == n ? ((uint32_t)g << 16) : 0u);      // G's left border at its last row is -g
+            uint32_t tt[NCOL];
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) tt[c] = (c == 0 ? diag : Wc[c - 1]) + en[c];
+            fetch_words(en, cfn, cgn);
+            cf_cur = cfn;
+            cfn = lds_u8(pf); cgn = lds_u8(pg);
+            if (st + 2 < n) { pf += kRowTile; pg -= kRowTile; }
 #pragma unroll
             for (int c = 0; c < NCOL; ++c) {
                 left = __vimax3_u16x2(tt[c], Wc[c], left);

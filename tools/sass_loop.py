@@ -33,6 +33,7 @@ def main():
     ap.add_argument("kernel")
     ap.add_argument("--listing")
     ap.add_argument("--min-dp", type=int, default=24)
+    ap.add_argument("--all", action="store_true", help="every innermost loop that qualifies, not only the shortest")
     args = ap.parse_args()
     lines = kernel_sass(args.kernel)
     if not lines:
@@ -45,7 +46,7 @@ def main():
         m = LINE.match(line)
         if m:
             inst.append((int(m.group(1), 16), m.group(2).strip()))
-    best = None
+    loops = []
     for addr, text in inst:
         m = re.search(r"\bBRA\s+(0x[0-9a-f]+)", text)
         if not m:
@@ -55,18 +56,22 @@ def main():
             continue
         body = [t for a, t in inst if target <= a <= addr]
         dp = sum("VIMNMX3" in t for t in body)
-        if dp >= args.min_dp and (best is None or len(body) < len(best[2])):
-            best = (target, addr, body)
-    if best is None:
+        if dp >= args.min_dp:
+            loops.append((target, addr, body))
+    # innermost only: drop loops that contain another qualifying loop
+    loops = [l for l in loops if not any(o is not l and l[0] <= o[0] and o[1] <= l[1] for o in loops)]
+    if not loops:
         sys.exit("no loop with >= %d VIMNMX3 found" % args.min_dp)
-    target, addr, body = best
-    ops = collections.Counter()
-    for t in body:
-        t = re.sub(r"^@!?U?P\d+\s+", "", t)
-        ops[t.split()[0]] += 1
-    print("%s: loop 0x%04x..0x%04x, %d instructions" % (args.kernel, target, addr, len(body)))
-    for op, n in sorted(ops.items(), key=lambda kv: -kv[1]):
-        print("  %-22s %3d" % (op, n))
+    if not args.all:
+        loops = [min(loops, key=lambda l: len(l[2]))]
+    for target, addr, body in loops:
+        ops = collections.Counter()
+        for t in body:
+            t = re.sub(r"^@!?U?P\d+\s+", "", t)
+            ops[t.split()[0]] += 1
+        print("%s: loop 0x%04x..0x%04x, %d instructions" % (args.kernel, target, addr, len(body)))
+        for op, n in sorted(ops.items(), key=lambda kv: -kv[1]):
+            print("  %-22s %3d" % (op, n))
 
 
 if __name__ == "__main__":
