@@ -230,3 +230,30 @@ def test_module_entry_point_runs_the_reference_cli(tmp_path):
                               cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
         assert proc.returncode == 0, proc.stderr[-2000:]
         assert proc.stdout == want
+
+
+@pytest.mark.parametrize("options", [["--no-batch"], ["--dual"], ["--min-score", "75", "-k", "NBD103/NBD104"],
+                                     ["--detect-middle", "-k", "RBK004"], ["--no-batch", "--dual", "--trim"]])
+def test_cli_option_matrix_on_top_of_the_dropin(tmp_path, options):
+    """The CLI switches that change what the scanner is asked (cli.py:445-563: --no-batch -> per-read detect_barcode,
+    --dual, --min-score, --detect-middle): same TSV and same output stream with and without the drop-in."""
+    refloader.load()
+    from qcat import scanner as ref_scanner
+    from qcat_b200 import dropin
+    dropin.uninstall()
+    kit = options[options.index("-k") + 1] if "-k" in options else "RBK004"
+    layouts = ref_scanner.factory(mode="dual" if "--dual" in options else "epi2me", kit=None if "--dual" in options else kit).layouts
+    reads = _reads(layouts, 260, seed=41)
+    fastq = tmp_path / "reads.fastq"
+    with open(fastq, "w") as fh:
+        for i, r in enumerate(reads):
+            fh.write("@read%d\n%s\n+\n%s\n" % (i, r, "5" * len(r)))
+    argv = ["-f", str(fastq), "--min-read-length", "120"] + options
+    want = (_run_cli(argv + ["--tsv"]), _run_cli(argv))
+    dropin.install(device=0)
+    try:
+        got = (_run_cli(argv + ["--tsv"]), _run_cli(argv))
+    finally:
+        dropin.uninstall()
+    assert got == want
+    assert want[0].count("\n") > 200
