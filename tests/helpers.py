@@ -217,3 +217,46 @@ class OraclePlan(object):
             out[...] = got
             got = out
         return (got, kits) if return_kits else got
+
+
+def random_kit(rng, layout_cls, barcode_cls, double=False):
+    """Random kit geometry for fuzzing (a `random.Random`): 1-4 layouts with flanks of 0-45 nt, barcode placeholders of
+    12-30 nt, 1-40 barcodes per set -- some sets sharing a prefix / suffix (the shared-context columns then reach into
+    the barcodes), some layouts differing only in one flank base.  Built from the given AdapterLayout / Barcode
+    classes, so the same kit can be made of the reference's objects and of qcat_b200's mirrors."""
+    def seq(n):
+        return "".join(rng.choice("ACGT") for _ in range(n))
+
+    def barcode_set(length, count):
+        share_head = seq(rng.choice([0, 0, 2, 5]))[:length - 1]
+        share_tail = seq(rng.choice([0, 0, 3]))[:max(0, length - 1 - len(share_head))]
+        out, seen = [], set()
+        while len(out) < count:
+            s = share_head + seq(length - len(share_head) - len(share_tail)) + share_tail
+            if s not in seen:
+                seen.add(s)
+                out.append(barcode_cls("barcode%02d" % (len(out) + 1), len(out) + 1, s, True))
+        return out
+
+    layouts = []
+    n_layouts = rng.randrange(1, 5)
+    blen = rng.choice([12, 16, 20, 24, 24, 24, 27, 30])
+    count = rng.choice([1, 2, 3, 7, 12, 24, 33, 40])
+    set1 = barcode_set(blen, count)
+    set2 = barcode_set(rng.choice([16, 24]), rng.choice([2, 5, 24])) if double else None
+    base_left, base_mid, base_right = seq(rng.randrange(0, 46)), seq(rng.randrange(4, 25)), seq(rng.randrange(0, 46))
+    for li in range(n_layouts):
+        left, right = base_left, base_right
+        if li and rng.random() < 0.5:                      # a sibling layout: one flank base changed
+            if left:
+                p = rng.randrange(len(left))
+                left = left[:p] + rng.choice("ACGT") + left[p + 1:]
+        elif li:
+            left, right = seq(rng.randrange(0, 46)), seq(rng.randrange(0, 46))
+        sequence = left + "N" * blen
+        if double:
+            sequence += base_mid + "N" * len(set2[0].sequence)
+        sequence += right
+        layouts.append(layout_cls("KIT%d" % li, sequence, set1 if li % 2 == 0 else barcode_set(blen, count), set2,
+                                  "random kit %d" % li))
+    return layouts
