@@ -313,15 +313,22 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, ui
 #endif
 constexpr int kBarcodeMaxWarps = QCB_BC_MAXWARPS;
 
-struct BarcodeTileSlot {            // per row-tile buffer, written by warp 0
-    int4 meta[kRowTile];            // taskmeta of the tile's 32 slots
-    long long tile;                 // tile index, -1 = no more tiles for this CTA
-    unsigned long long bar;         // mbarrier the bulk copy completes on
+constexpr int kMaxTilesPerIter = 2;
+struct BarcodeTileSlot {            // per row-tile buffer (one group of tiles_per_iter consecutive tiles), written by warp 0
+    int4 meta[kMaxTilesPerIter][kRowTile];   // taskmeta of the tiles' 32 slots
+    long long group;                // tile-group index, -1 = no more groups for this CTA
+    unsigned long long bar;         // mbarrier the bulk copies complete on
+    int nmax[kMaxTilesPerIter];     // longest region of each tile, -1 = the tile is not taken by this launch
 };
+struct BarcodeStage {               // warp 0's look-ahead: the taskmeta of the next candidate group, copied asynchronously
+    int4 meta[kMaxTilesPerIter][kRowTile];
+    long long cand;                 // the next group index to look at
+};
+constexpr size_t kBarcodeSlotBytes = 2 * sizeof(BarcodeTileSlot) + sizeof(BarcodeStage);
 
 __global__ void __launch_bounds__(kBarcodeMaxWarps * 32, QCB_BC_MINBLOCKS)
 k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, int rows_min, int rows_cap, int one_set,
-               int smem_profile_bytes, const uint32_t *__restrict__ rowinfo, const int4 *__restrict__ taskmeta,
+               int tiles_per_iter, int smem_profile_bytes, const uint32_t *__restrict__ rowinfo, const int4 *__restrict__ taskmeta,
                int32_t *__restrict__ bc_score, const unsigned int *__restrict__ bucket_counts, int pass)
 {
     // rows_cap = DP rows (0..n) one shared-memory row tile of this launch holds; a tile is taken when its longest region
@@ -334,8 +341,9 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
     uint8_t *smem = smem_bc;
     uint32_t *s_prof = (uint32_t *)smem;                             // [pair][code][kProfRowBytes], 1 KB per pair
     const int tile_bytes = rows_cap * kRowTile * 4;
-    uint8_t *s_rows = smem + smem_profile_bytes;                     // two row tiles: [2][rows_cap][32] row-info words
-    BarcodeTileSlot *s_slot = (BarcodeTileSlot *)(s_rows + 2 * tile_bytes);
+    uint8_t *s_rows = smem + smem_profile_bytes;                     // row tiles: [2][tiles_per_iter][rows_cap][32] row-info words
+    BarcodeTileSlot *s_slot = (BarcodeTileSlot *)(s_rows + 2 * tiles_per_iter * tile_bytes);
+    BarcodeStage *s_stage = (BarcodeStage *)(s_slot + 2);
     const uint32_t prof_addr = (uint32_t)__cvta_generic_to_shared(s_prof);
     const uint32_t rows_addr = (uint32_t)__cvta_generic_to_shared(s_rows);
 
@@ -352,7 +360,11 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
     long long tile_begin = 0, n_tiles = (n_tasks + kRowTile - 1) / kRowTile;
     if (pass == 0) n_tiles = min(n_tiles, ((long long)bucket_counts[0] + kRowTile - 1) / kRowTile);
     if (pass == 1) tile_begin = (n_tasks - (long long)bucket_counts[1]) / kRowTile;
-    if (tile_begin + blockIdx.x >= n_tiles) return;           // nothing for this CTA (before it loads any profile)
+    // A CTA iteration takes a group of tiles_per_iter consecutive tiles (1 or 2): with two, a 12-pair set gives the 8 warps
+    // 24 items (three full rounds instead of 8 + 4) and the tile switch is paid half as often.
+    const int tpi = tiles_per_iter;
+    const long long group_begin = tile_begin / tpi, n_groups = (n_tiles + tpi - 1) / tpi;
+    if (group_begin + blockIdx.x >= n_groups) return;          // nothing for this CTA (before it loads any profile)
 
     if (threadIdx.x == 0) {
         mbar_init((uint32_t)__cvta_generic_to_shared(&s_slot[0].bar), 1);
@@ -361,60 +373,96 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
     }
     __syncthreads();
 
-    // warp 0: find the next tile of this CTA at or after `cand` that this launch takes, start its bulk copy into buffer
-    // b and publish its metadata; returns the candidate after it.  meta_c = taskmeta of `cand` (loaded by the caller).
-    auto fetch = [&](long long cand, int4 meta_c, int b) -> long long {
-        for (;;) {
-            if (cand >= n_tiles) {
-                if (lane == 0) s_slot[b].tile = -1;
-                return cand;
-            }
-            const int n_c = meta_c.y < 0 ? 0 : meta_c.x;
-            const int nmax_c = __reduce_max_sync(0xffffffffu, n_c);
-            if (nmax_c >= rows_min && nmax_c < rows_cap) {
-                s_slot[b].meta[lane] = meta_c;
-                if (lane == 0) {
-                    s_slot[b].tile = cand;
-                    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_slot[b].bar);
-                    const uint32_t bytes = (uint32_t)(nmax_c + 1) * kRowTile * 4;
-                    mbar_expect_tx(bar, bytes);
-                    bulk_load(rows_addr + (uint32_t)(b * tile_bytes), rowinfo + cand * (long long)(kRows * kRowTile), bytes, bar);
-                }
-                return cand + gridDim.x;
-            }
-            cand += gridDim.x;                                       // not for this launch: look at the next one
-            if (cand < n_tiles) {
-                const long long slot = cand * kRowTile + lane;
-                meta_c = slot < n_tasks ? taskmeta[slot] : make_int4(0, -1, 0, 0);
-            }
+    // warp 0: start the asynchronous copy of a group's taskmeta into the staging area (no registers held meanwhile)
+    auto stage_meta = [&](long long group) {
+#pragma unroll
+        for (int j = 0; j < kMaxTilesPerIter; ++j) {
+            const long long tile = group * tpi + j;
+            const long long slot = tile * kRowTile + lane;
+            if (j < tpi && group < n_groups && tile < n_tiles && slot < n_tasks)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;"
+                             ::"r"((uint32_t)__cvta_generic_to_shared(&s_stage->meta[j][lane])), "l"(taskmeta + slot) : "memory");
+            else
+                s_stage->meta[j][lane] = make_int4(0, -1, 0, 0);
         }
     };
-    auto load_meta = [&](long long tile) -> int4 {
-        const long long slot = tile * kRowTile + lane;
-        return (tile < n_tiles && slot < n_tasks) ? taskmeta[slot] : make_int4(0, -1, 0, 0);
+    // warp 0: find the next group of this CTA at or after the staged candidate in which this launch takes a tile, start the
+    // bulk copies into buffer b, publish the metadata, and stage the candidate after it
+    auto fetch = [&](int b) {
+        long long cand = s_stage->cand;
+        for (;;) {
+            if (cand >= n_groups) {
+                if (lane == 0) s_slot[b].group = -1;
+                break;
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            int4 meta_c[kMaxTilesPerIter];
+            int nm[kMaxTilesPerIter];
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < kMaxTilesPerIter; ++j) {
+                meta_c[j] = s_stage->meta[j][lane];
+                const int n_c = meta_c[j].y < 0 ? 0 : meta_c[j].x;
+                const int nmax_c = __reduce_max_sync(0xffffffffu, n_c);
+                const bool take = j < tpi && nmax_c >= rows_min && nmax_c < rows_cap;
+                nm[j] = take ? nmax_c : -1;
+                any = any || take;
+            }
+            if (any) {
+#pragma unroll
+                for (int j = 0; j < kMaxTilesPerIter; ++j)
+                    if (j < tpi) s_slot[b].meta[j][lane] = meta_c[j];
+                __syncwarp();
+                if (lane == 0) {
+                    s_slot[b].group = cand;
+                    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_slot[b].bar);
+                    uint32_t bytes = 0;
+#pragma unroll
+                    for (int j = 0; j < kMaxTilesPerIter; ++j) {
+                        s_slot[b].nmax[j] = nm[j];
+                        if (nm[j] >= 0) bytes += (uint32_t)(nm[j] + 1) * kRowTile * 4;
+                    }
+                    mbar_expect_tx(bar, bytes);
+#pragma unroll
+                    for (int j = 0; j < kMaxTilesPerIter; ++j)
+                        if (nm[j] >= 0)
+                            bulk_load(rows_addr + (uint32_t)((b * tpi + j) * tile_bytes),
+                                      rowinfo + (cand * tpi + j) * (long long)(kRows * kRowTile), (uint32_t)(nm[j] + 1) * kRowTile * 4, bar);
+                }
+                cand += gridDim.x;
+                stage_meta(cand);
+                break;
+            }
+            cand += gridDim.x;                                       // nothing for this launch in it: look at the next one
+            stage_meta(cand);
+        }
+        __syncwarp();
+        if (lane == 0) s_stage->cand = cand;
+        __syncwarp();
     };
 
-    long long cand = tile_begin + blockIdx.x;  // warp 0: the next tile index to look at
-    int4 meta_next = make_int4(0, -1, 0, 0);   // warp 0: its taskmeta, loaded one tile ahead of its use
     if (warp == 0) {
-        cand = fetch(cand, load_meta(cand), 0);
-        meta_next = load_meta(cand);
+        if (lane == 0) s_stage->cand = group_begin + blockIdx.x;
+        __syncwarp();
+        stage_meta(group_begin + blockIdx.x);
+        fetch(0);
     }
     __syncthreads();
 
+    const int n_warps = (int)(blockDim.x >> 5);
     for (unsigned it = 0;; ++it) {
         const int b = (int)(it & 1);
-        const long long tile = s_slot[b].tile;
-        if (tile < 0) break;
+        if (s_slot[b].group < 0) break;
         // buffer b ^ 1 was last read in the previous iteration, which every warp has left: refill it
-        if (warp == 0) {
-            cand = fetch(cand, meta_next, b ^ 1);
-            meta_next = load_meta(cand);
-        }
-        const int4 meta = s_slot[b].meta[lane];
+        if (warp == 0) fetch(b ^ 1);
         mbar_wait((uint32_t)__cvta_generic_to_shared(&s_slot[b].bar), (it >> 1) & 1u);
-        const uint32_t row_addr = rows_addr + (uint32_t)(b * tile_bytes);
-        const uint32_t *s_row = (const uint32_t *)(s_rows + b * tile_bytes);
+        int item_off = 0;                      // items (tile, pair) handed out so far in this iteration, modulo the warp count
+      for (int j = 0; j < tpi; ++j) {
+        if (s_slot[b].nmax[j] < 0) continue;   // uniform over the CTA
+        const int4 meta = s_slot[b].meta[j][lane];
+        const uint32_t row_addr = rows_addr + (uint32_t)((b * tpi + j) * tile_bytes);
+        const uint32_t *s_row = (const uint32_t *)(s_rows + (b * tpi + j) * tile_bytes);
         const FastGroup G = f.groups[meta.y < 0 ? 0 : meta.y];
         const int n_task = meta.y < 0 ? 0 : meta.x;
         long long w; int k;
@@ -447,7 +495,10 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
             }
             const int nmax = __reduce_max_sync(0xffffffffu, n);
             const int npairs_max = __reduce_max_sync(0xffffffffu, n > 0 ? npairs : 0);
-            for (int pr = warp; pr < npairs_max; pr += (int)(blockDim.x >> 5)) {
+            int first = warp - item_off;                                      // this warp's first pair of the tile
+            if (first < 0) first += n_warps;
+            item_off = (item_off + npairs_max) % n_warps;
+            for (int pr = first; pr < npairs_max; pr += n_warps) {
                 const int pcl = min(pr, npairs - 1);
                 const uint32_t block = prof_addr + set_base + (uint32_t)pcl * kProfPairBytes;
                 uint32_t Wc[kCore];
@@ -493,6 +544,7 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
                 }
             }
         }
+      }
         __syncthreads();                       // every warp is done with buffer b; warp 0's slot b ^ 1 is published
     }
 }

@@ -74,6 +74,7 @@ struct FastPlan {
     int sm_count = 0;
     size_t barcode_smem = 0;
     int max_pairs = 1;               // barcode pairs of the largest template group
+    std::vector<int> group_pairs;    // barcode pairs of every template group
     bool one_set = false;            // k_barcode_fast keeps one core set's profile in shared memory at a time (many kits)
     size_t profile_smem = 0;         // bytes of the profile region of k_barcode_fast's shared memory
     int short_rows = 0;              // > 0: row-tile size of the first of two k_barcode_fast launches (dual mode)
@@ -401,6 +402,7 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
 {
     fp.sm_count = sm_count;
     fp.adapter_ok = fp.barcode_ok = false;
+    fp.group_pairs.clear();
     if (h->mode == QCB_MODE_SIMPLE) return 0;       // simple mode runs on the generic kernels (needs end_query per barcode)
     fast_adapter_prepare(fp, h);
     fp.barcode_ok = false;
@@ -450,6 +452,7 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
         if (smax * tlen + (kFastMaxStride + tlen) * g + 64 >= 2048) return 0;       // F / G are packed into 11 bits
         G.u = u; G.d = d; G.pad = kCore - core; G.tlen = tlen; G.nb = nb;
         fp.max_pairs = std::max(fp.max_pairs, (nb + 1) / 2);
+        fp.group_pairs.push_back((nb + 1) / 2);
         G.up_off = (int32_t)ctx.size();
         for (int j = 0; j < u; ++j) ctx.push_back(h->bmap[first[j]]);
         G.down_off = (int32_t)ctx.size();
@@ -557,7 +560,7 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     // many sets (`-k auto`: every kit's) keep only the set of the tile at hand in shared memory.
     fp.one_set = profile_bytes > 64 * 1024;
     fp.profile_smem = fp.one_set ? (size_t)fp.max_pairs * kProfPairBytes : profile_bytes;
-    fp.barcode_smem = fp.profile_smem + 2 * (size_t)kRows * kRowTile * 4 + 2 * sizeof(BarcodeTileSlot);
+    fp.barcode_smem = fp.profile_smem + 2 * (size_t)kRows * kRowTile * 4 + kBarcodeSlotBytes;   // one tile per iteration always fits
     if (fp.barcode_smem > 220 * 1024) return 0;
     // Opt every packed kernel into the device's full dynamic shared memory once.  The attribute is a per-device, per-
     // kernel maximum shared by all plans of the process, so it must never be lowered to one plan's own need.
@@ -741,29 +744,41 @@ inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, long long n_wind
     const uint32_t *rowinfo = (const uint32_t *)fp.rowinfo;
     const int4 *taskmeta = (const int4 *)fp.taskmeta;
     {
-        // warps per CTA: every warp takes one barcode pair per round, so pick the count (<= 12) that wastes the fewest
-        // warp-rounds for this plan's largest set (6 pairs -> 6 warps, 48 pairs -> 12 warps), preferring more warps
-        int warps = kBarcodeMaxWarps, best_waste = 1 << 30;
-        for (int wc = kBarcodeMaxWarps; wc >= 4; --wc) {
-            int waste = (fp.max_pairs + wc - 1) / wc * wc - fp.max_pairs;
-            if (waste < best_waste) { best_waste = waste; warps = wc; }
-        }
         cudaFuncAttributes attr;
         if (cudaFuncGetAttributes(&attr, k_barcode_fast) != cudaSuccess) return 1;
-        const size_t regs_per_cta = (size_t)warps * 32 * ((attr.numRegs + 7) / 8 * 8);
         const size_t profile_bytes = fp.profile_smem;
         const int passes = fp.short_rows > 0 ? 2 : 1;
         for (int pass = 0; pass < passes; ++pass) {
             const int rows_min = pass == 0 ? 1 : fp.short_rows;
             const int rows_cap = (passes == 2 && pass == 0) ? fp.short_rows : kRows;
-            // shared memory: profile | two row tiles (double buffered) | two tile slots
-            const size_t smem = profile_bytes + 2 * (size_t)rows_cap * kRowTile * 4 + 2 * sizeof(BarcodeTileSlot);
-            int ctas_per_sm = (int)std::min<size_t>((220 * 1024) / std::max<size_t>(1, smem + 1024), 65536 / regs_per_cta);
-            ctas_per_sm = std::max(1, std::min(ctas_per_sm, std::min(8, 2048 / (warps * 32))));
-            int grid = (int)std::min<long long>(n_tiles, (long long)fp.sm_count * ctas_per_sm);
+            // Every warp takes one (tile, barcode pair) item per round: the warp count (<= kBarcodeMaxWarps) that wastes
+            // the fewest warp-rounds on the plan's largest set, preferring more warps.  When a smaller set of the plan
+            // still leaves warps idle at that count (dual: 12 pairs on 8 warps), a CTA iteration takes two tiles -- if
+            // that fills the rounds and costs no CTA per SM (shared memory: profile | double-buffered row tiles | slots).
+            int warps = kBarcodeMaxWarps, best_waste = 1 << 30;
+            for (int wc = kBarcodeMaxWarps; wc >= 4; --wc) {
+                const int waste = (fp.max_pairs + wc - 1) / wc * wc - fp.max_pairs;
+                if (waste < best_waste) { best_waste = waste; warps = wc; }
+            }
+            const size_t regs_per_cta = (size_t)warps * 32 * ((attr.numRegs + 7) / 8 * 8);
+            const int by_regs = std::max<int>(1, std::min<int>((int)(65536 / regs_per_cta), std::min(8, 2048 / (warps * 32))));
+            auto smem_for = [&](int t) { return profile_bytes + 2 * (size_t)t * rows_cap * kRowTile * 4 + kBarcodeSlotBytes; };
+            static const int forced_tpi = getenv("QCB_BC_TPI") ? atoi(getenv("QCB_BC_TPI")) : 0;     // A/B switch (1 or 2)
+            int tpi = 1;
+            bool idle = false, filled = true;
+            for (int np : fp.group_pairs) {
+                idle = idle || np % warps != 0;
+                filled = filled && (2 * np) % warps == 0;
+            }
+            if (idle && filled && (int)((220 * 1024) / (smem_for(2) + 1024)) >= by_regs) tpi = 2;
+            if (forced_tpi >= 1 && forced_tpi <= kMaxTilesPerIter) tpi = forced_tpi;
+            const size_t smem = smem_for(tpi);
+            const int ctas_per_sm = std::max(1, std::min((int)((220 * 1024) / (smem + 1024)), by_regs));
+            const long long n_groups = (n_tiles + tpi - 1) / tpi;
+            int grid = (int)std::min<long long>(n_groups, (long long)fp.sm_count * ctas_per_sm);
             const unsigned int *bucket_counts = (const unsigned int *)((const uint8_t *)fp.perm + (size_t)n_tiles * kRowTile * 4);
             k_barcode_fast<<<grid, warps * 32, smem, st>>>(fp.dev, n_windows, dual, bmax0, bslots, rows_min, rows_cap, fp.one_set ? 1 : 0,
-                                                           (int)profile_bytes, rowinfo, taskmeta, bc_score, bucket_counts,
+                                                           tpi, (int)profile_bytes, rowinfo, taskmeta, bc_score, bucket_counts,
                                                            passes == 2 ? pass : -1);
             ++*launches;
         }
