@@ -542,7 +542,7 @@ def compute_roofline(w, step_ms, dom, dom_ms, clocks, local_rank, args):
             compute["smem_gather_roofline"] = {"kernel": "k_barcode_fast", "unit": "shared-memory wavefronts/s",
                                                "wavefronts_per_read": wavefronts_per_read, "achieved": achieved_wf,
                                                "peak": peak_wf, "frac": achieved_wf / peak_wf,
-                                               "evidence": "profiles/r02_barcode_full.md"}
+                                               "evidence": "profiles/r02_pbc096_full.md"}
     return compute
 
 
