@@ -349,7 +349,8 @@ class Workload(object):
             self.step()
         if self.world > 1:                                     # warm the communicator outside the timed region
             import torch.distributed as dist
-            dist.all_gather([torch.zeros_like(self.d_counts) for _ in range(self.world)], self.d_counts)
+            gathered = torch.zeros(self.world * self.n_bins, dtype=self.d_counts.dtype, device=self.dev)
+            dist.all_gather_into_tensor(gathered, self.d_counts)
         self.barrier()
         self.d_counts.zero_()
         launches0 = self.plan.info()["kernel_launches"]
@@ -364,17 +365,30 @@ class Workload(object):
             dist.all_reduce(torch.zeros(1, device=self.dev))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        marks = []
         for _ in range(steps):
             self.step()
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
+        e_mid = marks[-1]
         if self.world > 1:
-            gathered = [torch.zeros_like(self.d_counts) for _ in range(self.world)]
-            dist.all_gather(gathered, self.d_counts)          # the path's only collective: per-barcode counts, once
-            total_counts = torch.stack(gathered).sum(0)
+            dist.all_gather_into_tensor(gathered, self.d_counts)   # the path's only collective: per-barcode counts, once
+            total_counts = gathered.view(self.world, self.n_bins).sum(0)
         else:
             total_counts = self.d_counts
         e1.record()
         self.barrier()
-        elapsed_ms = self.max_over_ranks(e0.elapsed_time(e1))
+        mine = e0.elapsed_time(e1)
+        self.gather_ms = e_mid.elapsed_time(e1)                # the count all-gather (+ waiting for the slowest rank)
+        elapsed_ms = self.max_over_ranks(mine)
+        self.rank_ms = [mine]
+        self.rank_step_end_ms = [[e0.elapsed_time(m) for m in marks]]
+        if self.world > 1:                                     # every rank's own timeline, for the record
+            t = torch.tensor([mine] + self.rank_step_end_ms[0], dtype=torch.float64, device=self.dev)
+            parts = [torch.zeros_like(t) for _ in range(self.world)]
+            dist.all_gather(parts, t)
+            self.rank_ms = [float(x[0].item()) for x in parts]
+            self.rank_step_end_ms = [[round(float(v), 3) for v in x[1:].tolist()] for x in parts]
         launches = self.plan.info()["kernel_launches"] - launches0
         assert int(total_counts.sum().item()) == self.world * self.n * steps, "histogram does not account for every read"
         return elapsed_ms, total_counts, int(launches)
@@ -600,10 +614,8 @@ def strong_scaling(w, total_reads):
     e0.record()
     run()
     if w.world > 1:
-        import torch.distributed as dist
-        gathered = [torch.zeros_like(w.d_counts) for _ in range(w.world)]
-        dist.all_gather(gathered, w.d_counts)
-        total = int(torch.stack(gathered).sum().item())
+        from qcat_b200 import dist as qdist
+        total = int(qdist.allgather_counts(w.d_counts).sum().item())
     else:
         total = int(w.d_counts.sum().item())
     e1.record()
@@ -676,6 +688,7 @@ def run_ours(args):
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     elapsed_ms, total_counts, launches = head.timed(args.steps, args.warmup, sampler)
+    head_rank_ms, head_gather_ms, head_step_end = list(head.rank_ms), head.gather_ms, head.rank_step_end_ms
     clocks = sampler.stop() if rank == 0 else None
     step_ms = elapsed_ms / args.steps
     value = world * n * args.steps / (elapsed_ms * 1e-3)
@@ -730,6 +743,8 @@ def run_ours(args):
                 "config": workload_config(args.workload, head.spec, n), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "compute_roofline": compute, "cpu_baseline": cpu, "parity": parity,
                 "sharded_parity": sharded, "strong_scaling": strong, "workloads": extras,
+                "rank_ms_per_step": [ms / args.steps for ms in head_rank_ms], "count_allgather_ms": head_gather_ms,
+                "rank_step_end_ms": head_step_end if args.steps <= 8 else [r[:4] + r[-4:] for r in head_step_end],
                 "kernels": {"fast_adapter": info["fast_adapter"], "fast_barcode": info["fast_barcode"]}}
         emit_result(line)
     if world > 1:
