@@ -755,6 +755,7 @@ inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, long long n_wind
             // the fewest warp-rounds on the plan's largest set, preferring more warps.  When a smaller set of the plan
             // still leaves warps idle at that count (dual: 12 pairs on 8 warps), a CTA iteration takes two tiles -- if
             // that fills the rounds and costs no CTA per SM (shared memory: profile | double-buffered row tiles | slots).
+            // Plans that keep one core set resident stay on one tile (their set switches are CTA-wide).
             int warps = kBarcodeMaxWarps, best_waste = 1 << 30;
             for (int wc = kBarcodeMaxWarps; wc >= 4; --wc) {
                 const int waste = (fp.max_pairs + wc - 1) / wc * wc - fp.max_pairs;
@@ -770,7 +771,7 @@ inline int fast_barcode_stage(FastPlan &fp, const DevTables &t, long long n_wind
                 idle = idle || np % warps != 0;
                 filled = filled && (2 * np) % warps == 0;
             }
-            if (idle && filled && (int)((220 * 1024) / (smem_for(2) + 1024)) >= by_regs) tpi = 2;
+            if (idle && filled && !fp.one_set && (int)((220 * 1024) / (smem_for(2) + 1024)) >= by_regs) tpi = 2;
             if (forced_tpi >= 1 && forced_tpi <= kMaxTilesPerIter) tpi = forced_tpi;
             const size_t smem = smem_for(tpi);
             const int ctas_per_sm = std::max(1, std::min((int)((220 * 1024) / (smem + 1024)), by_regs));
