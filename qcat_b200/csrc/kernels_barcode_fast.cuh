@@ -458,93 +458,93 @@ k_barcode_fast(FastDev f, long long n_windows, int dual, int bmax0, int bslots, 
         if (warp == 0) fetch(b ^ 1);
         mbar_wait((uint32_t)__cvta_generic_to_shared(&s_slot[b].bar), (it >> 1) & 1u);
         int item_off = 0;                      // items (tile, pair) handed out so far in this iteration, modulo the warp count
-      for (int j = 0; j < tpi; ++j) {
-        if (s_slot[b].nmax[j] < 0) continue;   // uniform over the CTA
-        const int4 meta = s_slot[b].meta[j][lane];
-        const uint32_t row_addr = rows_addr + (uint32_t)((b * tpi + j) * tile_bytes);
-        const uint32_t *s_row = (const uint32_t *)(s_rows + (b * tpi + j) * tile_bytes);
-        const FastGroup G = f.groups[meta.y < 0 ? 0 : meta.y];
-        const int n_task = meta.y < 0 ? 0 : meta.x;
-        long long w; int k;
-        decode_task((long long)(uint32_t)meta.w, n_windows, dual, w, k);      // the task behind this slot
-        const int rup = meta.z;
-        const int npairs = (G.nb + 1) >> 1;
-        const int v = G.u + (kCore - G.pad);            // last core column (template coordinates)
-        int32_t *dst = bc_score + w * bslots + (k ? bmax0 : 0);
-        unsigned todo = __ballot_sync(0xffffffffu, n_task > 0);               // the same in every warp of the CTA
-        while (todo) {
-            int n = n_task;
-            uint32_t set_base = (uint32_t)G.prof_off;
-            if (one_set) {
-                const int set = __reduce_min_sync(0xffffffffu, (todo >> lane) & 1u ? G.prof_off : INT32_MAX);
-                const bool mine = ((todo >> lane) & 1u) && G.prof_off == set;
-                const unsigned m_mine = __ballot_sync(0xffffffffu, mine);
-                if (set != resident) {                                         // uniform over the CTA
-                    const int set_pairs = __shfl_sync(0xffffffffu, npairs, __ffs(m_mine) - 1);
-                    __syncthreads();                                           // every warp is done with the old set
-                    const uint32_t *src = f.profile + set / 4;
-                    for (int i = threadIdx.x; i < set_pairs * (kProfPairBytes / 4); i += blockDim.x) s_prof[i] = src[i];
-                    resident = set;
-                    __syncthreads();
+        for (int j = 0; j < tpi; ++j) {
+            if (s_slot[b].nmax[j] < 0) continue;   // uniform over the CTA
+            const int4 meta = s_slot[b].meta[j][lane];
+            const uint32_t row_addr = rows_addr + (uint32_t)((b * tpi + j) * tile_bytes);
+            const uint32_t *s_row = (const uint32_t *)(s_rows + (b * tpi + j) * tile_bytes);
+            const FastGroup G = f.groups[meta.y < 0 ? 0 : meta.y];
+            const int n_task = meta.y < 0 ? 0 : meta.x;
+            long long w; int k;
+            decode_task((long long)(uint32_t)meta.w, n_windows, dual, w, k);      // the task behind this slot
+            const int rup = meta.z;
+            const int npairs = (G.nb + 1) >> 1;
+            const int v = G.u + (kCore - G.pad);            // last core column (template coordinates)
+            int32_t *dst = bc_score + w * bslots + (k ? bmax0 : 0);
+            unsigned todo = __ballot_sync(0xffffffffu, n_task > 0);               // the same in every warp of the CTA
+            while (todo) {
+                int n = n_task;
+                uint32_t set_base = (uint32_t)G.prof_off;
+                if (one_set) {
+                    const int set = __reduce_min_sync(0xffffffffu, (todo >> lane) & 1u ? G.prof_off : INT32_MAX);
+                    const bool mine = ((todo >> lane) & 1u) && G.prof_off == set;
+                    const unsigned m_mine = __ballot_sync(0xffffffffu, mine);
+                    if (set != resident) {                                         // uniform over the CTA
+                        const int set_pairs = __shfl_sync(0xffffffffu, npairs, __ffs(m_mine) - 1);
+                        __syncthreads();                                           // every warp is done with the old set
+                        const uint32_t *src = f.profile + set / 4;
+                        for (int i = threadIdx.x; i < set_pairs * (kProfPairBytes / 4); i += blockDim.x) s_prof[i] = src[i];
+                        resident = set;
+                        __syncthreads();
+                    }
+                    if (!mine) n = 0;
+                    todo &= ~m_mine;
+                    set_base = 0;
+                } else {
+                    todo = 0;
                 }
-                if (!mine) n = 0;
-                todo &= ~m_mine;
-                set_base = 0;
-            } else {
-                todo = 0;
-            }
-            const int nmax = __reduce_max_sync(0xffffffffu, n);
-            const int npairs_max = __reduce_max_sync(0xffffffffu, n > 0 ? npairs : 0);
-            int first = warp - item_off;                                      // this warp's first pair of the tile
-            if (first < 0) first += n_warps;
-            item_off = (item_off + npairs_max) % n_warps;
-            for (int pr = first; pr < npairs_max; pr += n_warps) {
-                const int pcl = min(pr, npairs - 1);
-                const uint32_t block = prof_addr + set_base + (uint32_t)pcl * kProfPairBytes;
-                uint32_t Wc[kCore];
-#pragma unroll
-                for (int c = 0; c < kCore; ++c) Wc[c] = dup16((uint32_t)((G.u + max(0, c + 1 - G.pad)) * g));
-                const uint32_t info0 = s_row[lane];
-                uint32_t Fprev = dup16((info0 >> kRowFShift) & kRowFMask);
-                uint32_t acc = dup16((uint32_t)(v * g)) + dup16(info0 >> kRowGShift);  // join term of row 0
-                int i = 1;
-                while (i <= nmax) {
-                    // rows up to the next row at which some lane's region ends run without per-lane branching; a lane's
-                    // scores are taken at its own last row, so whatever it computes afterwards is never used
-                    const int ev = __reduce_min_sync(0xffffffffu, n >= i ? n : INT32_MAX);
-                    uint32_t rp = row_addr + (uint32_t)(i * kRowTile + lane) * 4u;
-                    const uint32_t rp_end = row_addr + (uint32_t)((ev + 1) * kRowTile + lane) * 4u;
-                    i = ev + 1;
-#pragma unroll 1
-                    do {
-                        const uint32_t info = lds32(rp);
-                        rp += kRowTile * 4;
-                        const uint32_t prow = block | (info & kRowCodeMask);
-                        const uint32_t Fi = dup16((info >> kRowFShift) & kRowFMask);
-                        const uint32_t Gi = dup16(info >> kRowGShift);
-                        uint32_t e[kCore];
-#pragma unroll
-                        for (int c = 0; c < kCore; c += 4) {
-                            const uint4 q = lds128(prow + c * 4);
-                            e[c] = q.x; e[c + 1] = q.y; e[c + 2] = q.z; e[c + 3] = q.w;
-                        }
-                        uint32_t left = Fi;
-                        uint32_t t = e[0] + Fprev;
-#pragma unroll
-                        for (int c = 0; c < kCore; ++c) {
-                            const uint32_t tn = c + 1 < kCore ? e[c + 1] + Wc[c] : 0u;   // next column's diagonal term first
-                            left = __vimax3_u16x2(t, Wc[c], left);
-                            Wc[c] = left;
-                            t = tn;
-                        }
-                        Fprev = Fi;
-                        acc = __viaddmax_u16x2(left, Gi, acc);
-                    } while (rp != rp_end);
-                    if (n == ev && pr < npairs) store_pair_scores(Wc, acc, G, n, g, rup, pr, dst);
+                const int nmax = __reduce_max_sync(0xffffffffu, n);
+                const int npairs_max = __reduce_max_sync(0xffffffffu, n > 0 ? npairs : 0);
+                int first = warp - item_off;                                      // this warp's first pair of the tile
+                if (first < 0) first += n_warps;
+                item_off = (item_off + npairs_max) % n_warps;
+                for (int pr = first; pr < npairs_max; pr += n_warps) {
+                    const int pcl = min(pr, npairs - 1);
+                    const uint32_t block = prof_addr + set_base + (uint32_t)pcl * kProfPairBytes;
+                    uint32_t Wc[kCore];
+    #pragma unroll
+                    for (int c = 0; c < kCore; ++c) Wc[c] = dup16((uint32_t)((G.u + max(0, c + 1 - G.pad)) * g));
+                    const uint32_t info0 = s_row[lane];
+                    uint32_t Fprev = dup16((info0 >> kRowFShift) & kRowFMask);
+                    uint32_t acc = dup16((uint32_t)(v * g)) + dup16(info0 >> kRowGShift);  // join term of row 0
+                    int i = 1;
+                    while (i <= nmax) {
+                        // rows up to the next row at which some lane's region ends run without per-lane branching; a lane's
+                        // scores are taken at its own last row, so whatever it computes afterwards is never used
+                        const int ev = __reduce_min_sync(0xffffffffu, n >= i ? n : INT32_MAX);
+                        uint32_t rp = row_addr + (uint32_t)(i * kRowTile + lane) * 4u;
+                        const uint32_t rp_end = row_addr + (uint32_t)((ev + 1) * kRowTile + lane) * 4u;
+                        i = ev + 1;
+    #pragma unroll 1
+                        do {
+                            const uint32_t info = lds32(rp);
+                            rp += kRowTile * 4;
+                            const uint32_t prow = block | (info & kRowCodeMask);
+                            const uint32_t Fi = dup16((info >> kRowFShift) & kRowFMask);
+                            const uint32_t Gi = dup16(info >> kRowGShift);
+                            uint32_t e[kCore];
+    #pragma unroll
+                            for (int c = 0; c < kCore; c += 4) {
+                                const uint4 q = lds128(prow + c * 4);
+                                e[c] = q.x; e[c + 1] = q.y; e[c + 2] = q.z; e[c + 3] = q.w;
+                            }
+                            uint32_t left = Fi;
+                            uint32_t t = e[0] + Fprev;
+    #pragma unroll
+                            for (int c = 0; c < kCore; ++c) {
+                                const uint32_t tn = c + 1 < kCore ? e[c + 1] + Wc[c] : 0u;   // next column's diagonal term first
+                                left = __vimax3_u16x2(t, Wc[c], left);
+                                Wc[c] = left;
+                                t = tn;
+                            }
+                            Fprev = Fi;
+                            acc = __viaddmax_u16x2(left, Gi, acc);
+                        } while (rp != rp_end);
+                        if (n == ev && pr < npairs) store_pair_scores(Wc, acc, G, n, g, rup, pr, dst);
+                    }
                 }
             }
         }
-      }
         __syncthreads();                       // every warp is done with buffer b; warp 0's slot b ^ 1 is published
     }
 }
