@@ -70,7 +70,8 @@ struct qcb_plan {
     std::vector<int32_t> h_group_off, h_group, h_tmpl_off, h_adapter_off;
     std::vector<int32_t> subset_cached;   // layout subset currently held in subset_dev
     std::vector<int32_t> bin_base_cached; // histogram bin bases currently held in misc
-    int bmax0 = 0, bmax1 = 0;        // largest barcode set 0 / set 1 over all layouts
+    int bmax0 = 0, bmax1 = 0;        // score slots of barcode set 0 / set 1: the largest set over all layouts, rounded up to 4
+    int max_group = 0;               // largest barcode set
     int max_adapter = 0, max_template = 0;
     FastPlan fast;                   // packed-kernel tables (kernels_fast.cuh)
     // workspace, sized per chunk of reads
@@ -175,6 +176,9 @@ int upload_tables(qcb_plan *p, const qcb_tables *h)
             if (k == 0) p->bmax0 = std::max(p->bmax0, sz); else p->bmax1 = std::max(p->bmax1, sz);
         }
     }
+    p->max_group = std::max(p->bmax0, p->bmax1);
+    p->bmax0 = (p->bmax0 + 3) / 4 * 4;       // score slots per window and set: multiples of 4, so that k_finalize reads
+    p->bmax1 = (p->bmax1 + 3) / 4 * 4;       // a window's scores with aligned 16-byte loads
     for (int b = 0; b < nt; ++b) p->max_template = std::max(p->max_template, h->tmpl_off[b + 1] - h->tmpl_off[b]);
     {
         // Base classes of the 4-bit window format: bytes with equal (adapter code, barcode code) as they stand and
@@ -724,7 +728,7 @@ int qcb_plan_info(qcb_plan *p, qcb_plan_info_t *out)
     out->device = p->device; out->sm_count = p->sm_count;
     out->fast_adapter = (!p->force_generic && p->fast.adapter_ok) ? 1 : 0;
     out->fast_barcode = (!p->force_generic && p->fast.barcode_ok) ? 1 : 0;
-    out->max_group_size = std::max(p->bmax0, p->bmax1);
+    out->max_group_size = p->max_group;
     out->n_templates = p->t.n_templates;
     out->workspace_bytes = (int64_t)(p->wins.bytes + p->ad_score.bytes + p->ad_end.bytes + p->sel.bytes + p->bc_score.bytes +
                                      p->in_stage2[0].bytes + p->in_stage2[1].bytes + p->out_stage2[0].bytes + p->out_stage2[1].bytes + p->fast.workspace_bytes());

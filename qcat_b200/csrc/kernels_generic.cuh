@@ -411,10 +411,17 @@ __device__ __forceinline__ void pick_barcode(const DevTables &t, int g, int rlen
     if (tl_all > 0) {
         // every template of the group has the same length: score * 100.0 / tlen is strictly increasing in the integer
         // score and is 0.0 exactly for score 0, so the rule can run on the integers and divide once
+        // (scores of a window start on a 16-byte boundary: slot counts are multiples of 4 -- one load per four barcodes)
         bool have = false; int mx = 0, arg = -1;
-        for (int b = 0; b < cnt; ++b) {
-            const int sc = scores[b];
-            if (!have || mx == 0 || mx < sc) { have = true; mx = sc; arg = b; }
+        const int4 *quads = (const int4 *)scores;
+        for (int q = 0; q * 4 < cnt; ++q) {
+            const int4 v = quads[q];
+            const int sc4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int b = q * 4 + e, sc = sc4[e];
+                if (b < cnt && (!have || mx == 0 || mx < sc)) { have = true; mx = sc; arg = b; }
+            }
         }
         best = arg; best_score = (double)mx * 100.0 / (1.0 * (double)tl_all);
         return;
