@@ -258,8 +258,9 @@ __device__ __forceinline__ void store_pair_scores(const uint32_t (&Wc)[kCore], u
     const int bias_r = n * g + CB, bias_j = (n + G.tlen) * g;
     const int s0 = max(max((int)(rm & 0xffffu) - bias_r, (int)(acc & 0xffffu) - bias_j), rup);
     const int s1 = max(max((int)(rm >> 16) - bias_r, (int)(acc >> 16) - bias_j), rup);
-    dst[2 * pr] = s0;
-    if (2 * pr + 1 < G.nb) dst[2 * pr + 1] = s1;
+    // one 8-byte store: a window's score slots are padded to a multiple of four (api.cu), so slot 2 pr + 1 exists even
+    // when the group has an odd number of barcodes (it is never read then)
+    *(int2 *)(dst + 2 * pr) = make_int2(s0, s1);
 }
 
 // ---- bulk asynchronous copies (TMA's 1-D form: cp.async.bulk, completion counted on an mbarrier) --------------------
