@@ -94,7 +94,7 @@ struct FastPlan {
     std::vector<uint8_t> a_map;
     std::vector<std::vector<uint8_t>> a_seq;       // per layout adapter sequence (ASCII)
     std::vector<AdapterSubset *> subsets;
-    bool adapter_smem_configured[3] = {false, false, false};   // k_adapter_fast<NC> opted into full dynamic shared memory
+    bool adapter_smem_configured[4] = {false, false, false, false};   // k_adapter_fast<NC> opted into full dynamic shared memory
     int smem_optin = 0;              // cudaDevAttrMaxSharedMemoryPerBlockOptin of the plan's device
     size_t workspace_bytes() const
     {
@@ -126,14 +126,18 @@ constexpr int kAdapterPhase = 24;       // columns whose profile words are in re
 #ifndef QCB_AD48_BLOCKS
 #define QCB_AD48_BLOCKS 5
 #endif
+#ifndef QCB_AD56_BLOCKS
+#define QCB_AD56_BLOCKS 4
+#endif
 #ifndef QCB_AD64_BLOCKS
 #define QCB_AD64_BLOCKS 4
 #endif
 #ifndef QCB_AD104_BLOCKS
 #define QCB_AD104_BLOCKS 3
 #endif
+constexpr int adapter_blocks(int nc) { return nc <= 48 ? QCB_AD48_BLOCKS : (nc <= 56 ? QCB_AD56_BLOCKS : (nc <= 64 ? QCB_AD64_BLOCKS : QCB_AD104_BLOCKS)); }
 template <int NC>
-__global__ void __launch_bounds__(kAdapterWarps * 32, (NC <= 48 ? QCB_AD48_BLOCKS : (NC <= 64 ? QCB_AD64_BLOCKS : QCB_AD104_BLOCKS)))
+__global__ void __launch_bounds__(kAdapterWarps * 32, adapter_blocks(NC))
 k_adapter_fast(const uint32_t *__restrict__ profile, int profile_words, int row_words, int n_codes,
                const int4 *__restrict__ pair_meta, int npairs,
                const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ wlen, int wshift,
@@ -583,7 +587,7 @@ inline int fast_plan_build(FastPlan &fp, const qcb_tables *h, int sm_count)
     return 0;
 }
 
-inline int adapter_class_columns(int len) { return len <= 48 ? 48 : (len <= 64 ? 64 : 104); }
+inline int adapter_class_columns(int len) { return len <= 48 ? 48 : (len <= 56 ? 56 : (len <= 64 ? 64 : 104)); }
 
 inline AdapterSubset *adapter_subset(FastPlan &fp, const int32_t *h_subset, int n_subset, cudaStream_t st)
 {
@@ -593,9 +597,9 @@ inline AdapterSubset *adapter_subset(FastPlan &fp, const int32_t *h_subset, int 
     AdapterSubset *sub = new AdapterSubset();
     sub->key = key;
     const int nc = fp.a_codes, g = fp.a_gap;
-    // Templates are grouped by length class (48 / 64 / 104 register columns) and paired inside their class, shortest
+    // Templates are grouped by length class (48 / 56 / 64 / 104 register columns) and paired inside their class, shortest
     // first, so that a 39-nt adapter does not pay for the 90-nt one next to it in the subset (`-k auto`: 12 layouts).
-    for (int NC : {48, 64, 104}) {
+    for (int NC : {48, 56, 64, 104}) {
         std::vector<int> slots;
         for (int i = 0; i < n_subset; ++i)
             if (adapter_class_columns((int)fp.a_seq[key[i]].size()) == NC) slots.push_back(i);
@@ -641,7 +645,7 @@ inline int launch_adapter_fast(FastPlan &fp, AdapterSubset *sub, const AdapterCl
 {
     const size_t smem = cls.profile_bytes + (size_t)kAdapterWarps * kRows * kTile;
     // opt into the device's full dynamic shared memory (a per-device, per-kernel maximum shared by all plans: never lower it)
-    bool &configured = fp.adapter_smem_configured[NC <= 48 ? 0 : (NC <= 64 ? 1 : 2)];
+    bool &configured = fp.adapter_smem_configured[NC <= 48 ? 0 : (NC <= 56 ? 1 : (NC <= 64 ? 2 : 3))];
     if (!configured) {
         int dev = 0, optin = 0;
         if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -651,7 +655,7 @@ inline int launch_adapter_fast(FastPlan &fp, AdapterSubset *sub, const AdapterCl
     }
     const long long n_tiles = (n_windows + kTile - 1) / kTile;
     const long long n_tasks = n_tiles * cls.npairs;
-    int per_sm = NC <= 48 ? QCB_AD48_BLOCKS : (NC <= 64 ? QCB_AD64_BLOCKS : QCB_AD104_BLOCKS);
+    int per_sm = adapter_blocks(NC);
     while (per_sm > 1 && per_sm * smem > 200 * 1024) --per_sm;
     const int grid = (int)std::min<long long>((n_tasks + kAdapterWarps - 1) / kAdapterWarps, (long long)fp.sm_count * per_sm);
     if (grid <= 0) return 0;
@@ -674,6 +678,7 @@ inline int fast_adapter_stage(FastPlan &fp, const DevTables &, const uint8_t *co
     for (const AdapterClass &cls : sub->classes) {
         int rc;
         if (cls.nc_cols == 48) rc = launch_adapter_fast<48>(fp, sub, cls, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
+        else if (cls.nc_cols == 56) rc = launch_adapter_fast<56>(fp, sub, cls, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
         else if (cls.nc_cols == 64) rc = launch_adapter_fast<64>(fp, sub, cls, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
         else rc = launch_adapter_fast<104>(fp, sub, cls, codes, stride, wlen, wshift, n_windows, n_subset, ad_score, ad_end, st);
         if (rc) return rc;
